@@ -1,0 +1,179 @@
+/*
+ * rosdyn_b200.h -- C-ABI of the B200-native batched chain-dynamics engine.
+ *
+ * Drop-in boundary for the hot path of rosdyn_core's `rosdyn::Chain`
+ * (reference: rosdyn_core/include/rosdyn_core/primitives.h:235-555, implementation
+ * rosdyn_core/include/rosdyn_core/internal/primitives_impl.h:863-1391; abbreviated P.h / PI.h below).
+ * The reference has no FFI today (header-only C++ on Eigen); this is the set of entry points a
+ * reference-side binding would call instead of looping `Chain::get*` once per sample.
+ *
+ * Conventions (all mirrored from the reference):
+ *   - plain C types only; every entry returns an int32 status, never throws;
+ *   - the caller owns every buffer; the library owns only the opaque handle and its device workspace;
+ *   - batched arrays are SoA "planes": x[component][ld] with `ld >= n` samples, fp64;
+ *   - joint vectors q/Dq/DDq/DDDq have one plane per INPUT joint (input order, `S` of PI.h:708-731);
+ *   - 6-vectors are [linear(3); angular(3)] (spacevect_algebra.h:44-53), one block of 6 planes per link,
+ *     link 0 = base (always zero, PI.h:661-677);
+ *   - poses are 3x4 [R|p] row-major: plane r*4+c;
+ *   - matrices that the reference returns as Eigen column-major (Jacobian 6 x n, regressor n x 10*nJ,
+ *     inertia n x n) use plane index  col*rows + row;
+ *   - every batched evaluation is STATELESS: each sample is a fresh evaluation through the reference's
+ *     direct path (the reference's dirty-flag caches, PI.h:886/985/1088, are not reproduced);
+ *   - `stream` is a cudaStream_t passed as void*; device entry points are asynchronous on it.
+ *
+ * There is no CPU fallback: every compute entry fails with RDB_ERR_NO_DEVICE when no CUDA device exists.
+ */
+#ifndef ROSDYN_B200_H
+#define ROSDYN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDB_ABI_VERSION 1
+#define RDB_MAX_JOINTS 64 /* chain joints incl. fixed (reference: NUM_MAX_AXES 40, internal/types.h:126) */
+
+typedef int32_t rdb_status;
+enum
+{
+  RDB_OK = 0,
+  RDB_ERR_INVALID_ARG = 1,  /* null pointer, bad size, malformed descriptor                                  */
+  RDB_ERR_DIM_MISMATCH = 2, /* q/Dq/DDq not all present  (PI.h:1299-1309 throws std::invalid_argument)        */
+  RDB_ERR_CUDA = 3,         /* a CUDA runtime call failed; see rdb_last_error()                               */
+  RDB_ERR_NO_DEVICE = 4,    /* no CUDA device: the product path has no CPU fallback                           */
+  RDB_ERR_NOT_FOUND = 5,    /* "Base link not found"/"Tool link not found"/unknown link (PI.h:601-613,918-921) */
+  RDB_ERR_ALLOC = 6
+};
+
+enum
+{
+  RDB_JOINT_FIXED = 0,    /* rosdyn::Joint::FIXED,     T_pc = T_pj                               (PI.h:82-83) */
+  RDB_JOINT_REVOLUTE = 1, /* REVOLUTE and URDF continuous, R_jc = I + sin q K + (1-cos q) K^2    (PI.h:40-44) */
+  RDB_JOINT_PRISMATIC = 2 /* PRISMATIC, t = t_pj + axis_p q                                      (PI.h:45-46) */
+};
+
+/* One chain joint, as Joint::fromUrdf leaves it (PI.h:50-83). */
+typedef struct rdb_joint_desc
+{
+  int32_t type;        /* RDB_JOINT_*                                                                      */
+  int32_t input_index; /* position of this joint in q/Dq/DDq (column of S, PI.h:728), or -1: q == 0        */
+  double xyz[3];       /* parent->joint origin translation  t_pj                                            */
+  double rot[9];       /* parent->joint origin rotation R_pj, row-major (URDF rpy: Rz(y) Ry(p) Rx(r))       */
+  double axis[3];      /* joint axis in the joint frame; normalised on create when non-zero (PI.h:58-59)    */
+} rdb_joint_desc;
+
+/* One chain link, as Link::fromUrdf reads it (PI.h:288-319). */
+typedef struct rdb_link_desc
+{
+  double mass;
+  double cog[3];          /* inertial origin xyz in the link frame                                          */
+  double inertial_rot[9]; /* inertial-frame rotation R_p_cog, row-major (identity when rpy == 0)            */
+  double inertia[6];      /* ixx ixy ixz iyy iyz izz about the cog, in the inertial frame                   */
+} rdb_link_desc;
+
+/* A serial chain base->tool: n_joints joints (fixed ones INCLUDED, PI.h:638) and n_joints+1 links. */
+typedef struct rdb_chain_desc
+{
+  int32_t n_joints;
+  int32_t n_inputs; /* length of the joint vectors = number of input joints (PI.h:739)                      */
+  double gravity[3];
+  const rdb_joint_desc* joints; /* [n_joints], base -> tool                                                */
+  const rdb_link_desc* links;   /* [n_joints + 1], links[0] = base link (its inertia is never used)        */
+} rdb_chain_desc;
+
+typedef struct rdb_chain rdb_chain; /* opaque */
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int32_t rdb_abi_version(void);
+const char* rdb_last_error(void);       /* thread-local text of the last failure                            */
+const char* rdb_status_string(rdb_status s);
+int32_t rdb_device_count(void);         /* 0 when no CUDA device / driver                                   */
+uint64_t rdb_kernel_launch_count(void); /* kernels launched by this library since load (bench evidence)     */
+
+/* ---- chain handle (replaces rosdyn::createChain / Chain::init, PI.h:580-703, 1518-1527) ----------- */
+rdb_status rdb_chain_create(const rdb_chain_desc* desc, rdb_chain** out);
+void rdb_chain_destroy(rdb_chain* chain);
+/* Chain::setInputJointsName by index (PI.h:705-742): chain_joint_of_input[i] = chain joint fed by input i. */
+rdb_status rdb_chain_set_input_joints(rdb_chain* chain, int32_t n_inputs, const int32_t* chain_joint_of_input);
+int32_t rdb_chain_joints_number(const rdb_chain* chain);        /* Chain::getJointsNumber       P.h:381   */
+int32_t rdb_chain_links_number(const rdb_chain* chain);         /* Chain::getLinksNumber        P.h:377   */
+int32_t rdb_chain_active_joints_number(const rdb_chain* chain); /* Chain::getActiveJointsNumber P.h:385   */
+rdb_status rdb_chain_gravity(const rdb_chain* chain, double out[3]); /* Chain::getGravity P.h:409          */
+/* Chain::getNominalParameters (PI.h:1382-1391): out[10*n_joints], per link m, mcx,mcy,mcz, Ixx,Ixy,Ixz,Iyy,Iyz,Izz */
+rdb_status rdb_chain_nominal_parameters(const rdb_chain* chain, double* out);
+
+/* ---- batched inputs ------------------------------------------------------------------------------ */
+typedef struct rdb_samples
+{
+  int64_t n;          /* number of samples                                                                 */
+  int64_t ld;         /* plane stride (doubles), ld >= n                                                   */
+  const double* q;    /* [n_inputs][ld]                                                                    */
+  const double* dq;   /* [n_inputs][ld] or NULL (== 0)                                                     */
+  const double* ddq;  /* [n_inputs][ld] or NULL (== 0, e.g. getJointTorqueNonLinearPart PI.h:1285-1293)    */
+  const double* dddq; /* [n_inputs][ld] or NULL (== 0)                                                     */
+} rdb_samples;
+
+/* Kinematics outputs; every pointer is optional (NULL = not produced). nL = n_joints + 1. */
+typedef struct rdb_kinematics_out
+{
+  int64_t ld;             /* plane stride of every output below, ld >= n                                    */
+  double* T_tool;         /* [12][ld]        Chain::getTransformation            PI.h:884                   */
+  double* T_links;        /* [nL][12][ld]    Chain::getTransformations           PI.h:908                   */
+  double* jacobian;       /* [n_inputs*6][ld] Chain::getJacobian, plane col*6+row PI.h:927                  */
+  double* twist;          /* [nL][6][ld]     Chain::getTwist                     PI.h:981                   */
+  double* dtwist;         /* [nL][6][ld]     Chain::getDTwist                    PI.h:1082 (direct path)    */
+  double* dtwist_lin;     /* [nL][6][ld]     Chain::getDTwistLinearPart          PI.h:1029                  */
+  double* dtwist_nonlin;  /* [nL][6][ld]     Chain::getDTwistNonLinearPart       PI.h:1063                  */
+  double* ddtwist;        /* [nL][6][ld]     Chain::getDDTwist                   PI.h:1185 (direct path)    */
+  double* ddtwist_lin;    /* [nL][6][ld]     Chain::getDDTwistLinearPart         PI.h:1126 (correct buffer) */
+  double* ddtwist_nonlin; /* [nL][6][ld]     Chain::getDDTwistNonLinearPart      PI.h:1156                  */
+  double* torque;         /* [n_inputs][ld]  Chain::getJointTorque (no ext. wrench) PI.h:1277               */
+} rdb_kinematics_out;
+
+/* ---- batched device entry points (pointers are DEVICE pointers) ----------------------------------- */
+/* FK, Jacobian, twist / acceleration / jerk recursions and RNEA torque in one pass over the chain. */
+rdb_status rdb_kinematics_batch(const rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out, void* stream);
+
+/* Chain::getJointTorque(q,Dq,DDq) (PI.h:1277-1283): torque[n_inputs][ld_out]. */
+rdb_status rdb_torque_batch(const rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out, void* stream);
+
+/* Chain::getRegressor (PI.h:1295-1355): phi[(10*n_joints)*n_inputs][ld_out], plane col*n_inputs+row, every
+ * plane written (structural zeros are exact 0.0).  `torque` optional: getJointTorque of the same samples. */
+rdb_status rdb_regressor_batch(const rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, int64_t ld_out, void* stream);
+
+/* Chain::getJointInertia (PI.h:1357-1379): inertia[n_inputs*n_inputs][ld_out], plane col*n_inputs+row. */
+rdb_status rdb_inertia_batch(const rdb_chain* chain, const rdb_samples* in, double* inertia, int64_t ld_out, void* stream);
+
+/* Fused regressor -> normal equations (no reference code: the consumer rosdyn_identification is external,
+ * reference README.md:15).  With P = 10*n_joints and Phi_s the n_inputs x P regressor of sample s:
+ *   gram[P*P]  (+)= sum_s Phi_s^T Phi_s   (column-major, full symmetric matrix)
+ *   rhs[P]     (+)= sum_s Phi_s^T tau_s
+ *   tau_sq[1]  (+)= sum_s tau_s^T tau_s
+ * tau_s = tau_meas[n_inputs][ld] when given, else getJointTorque(q,Dq,DDq) of the sample.
+ * accumulate != 0 adds to the existing contents of gram/rhs/tau_sq (chunked / resumable use). */
+rdb_status rdb_regressor_gram_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+                                    double* tau_sq, int32_t accumulate, void* stream);
+
+/* ---- host-buffer convenience wrappers (pointers are HOST pointers; copies + sync inside) ---------- */
+rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out);
+rdb_status rdb_torque_batch_host(const rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out);
+rdb_status rdb_regressor_batch_host(const rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, int64_t ld_out);
+rdb_status rdb_inertia_batch_host(const rdb_chain* chain, const rdb_samples* in, double* inertia, int64_t ld_out);
+rdb_status rdb_regressor_gram_batch_host(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+                                         double* tau_sq, int32_t accumulate);
+
+/* ---- synthetic inputs (bench / tests): U(-1,1) from splitmix64, identical on host and device ------ */
+/* x[joint][i] = 2*(splitmix64(seed + 32*i + 8*stream + joint) >> 11) * 2^-53 - 1 ; stream 0..3 = q,Dq,DDq,DDDq */
+rdb_status rdb_fill_uniform(double* x, int32_t n_planes, int64_t n, int64_t ld, uint64_t seed, int32_t stream_id, void* stream);
+void rdb_fill_uniform_host(double* x, int32_t n_planes, int64_t n, int64_t ld, uint64_t seed, int32_t stream_id);
+
+/* FP64 pipe micro-benchmarks (own roofline denominator; MEASURED_PEAKS.json carries no FP64 figure).
+ * kind 0 = DFMA, 1 = DMMA m8n8k4.  Returns achieved TFLOP/s in *tflops (CUDA-event timed, best of reps). */
+rdb_status rdb_fp64_peak(int32_t kind, int32_t reps, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROSDYN_B200_H */

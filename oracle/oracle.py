@@ -1,0 +1,135 @@
+"""TEST INFRASTRUCTURE: ctypes loader of the CPU restatement oracle (oracle/rosdyn_oracle.c).
+
+Imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from rosdyn_b200.descriptor import CChainDesc, ChainDesc, to_ctypes  # interface structs only
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dbl_p = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement (gcc); a no-op when the .so is newer than the source."""
+    so = os.path.join(_HERE, "librosdyn_oracle.so")
+    src = os.path.join(_HERE, "rosdyn_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "all"])
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_dbl_p)
+
+
+class _Lib:
+    def __init__(self, fast: bool = False):
+        name = "librosdyn_oracle_fast.so" if fast else "librosdyn_oracle.so"
+        path = os.path.join(_HERE, name)
+        if not os.path.exists(path):
+            build()
+        self.lib = ctypes.CDLL(path)
+        L = self.lib
+        L.oracle_chain_create.restype = ctypes.c_void_p
+        L.oracle_chain_create.argtypes = [ctypes.POINTER(CChainDesc)]
+        L.oracle_chain_destroy.argtypes = [ctypes.c_void_p]
+        L.oracle_nominal_parameters.argtypes = [ctypes.c_void_p, _dbl_p]
+        L.oracle_max_threads.restype = ctypes.c_int
+        L.oracle_kind.restype = ctypes.c_char_p
+        i64, vp, ci = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int
+        L.oracle_kinematics_batch.argtypes = [vp, i64, i64] + [_dbl_p] * 4 + [i64] + [_dbl_p] * 11 + [ci]
+        L.oracle_regressor_torque_batch.argtypes = [vp, i64, i64, _dbl_p, _dbl_p, _dbl_p, i64, _dbl_p, _dbl_p, ci]
+        L.oracle_inertia_batch.argtypes = [vp, i64, i64, _dbl_p, i64, _dbl_p, ci]
+        L.oracle_regressor_gram.argtypes = [vp, i64, i64, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
+        L.oracle_fill_uniform.argtypes = [_dbl_p, ci, i64, i64, ctypes.c_uint64, ci]
+
+
+_libs = {}
+
+
+def lib(fast: bool = False) -> _Lib:
+    if fast not in _libs:
+        _libs[fast] = _Lib(fast)
+    return _libs[fast]
+
+
+def fill_uniform(n_planes: int, n: int, seed: int, stream_id: int) -> np.ndarray:
+    x = np.empty((n_planes, n))
+    lib().lib.oracle_fill_uniform(_ptr(x), n_planes, n, n, seed, stream_id)
+    return x
+
+
+def _c(a, rows=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    assert a.ndim == 2 and (rows is None or a.shape[0] == rows), (a.shape, rows)
+    return a
+
+
+class OracleChain:
+    """CPU restatement of rosdyn::Chain, batched over SoA arrays x[component][N] (same layout as the C-ABI)."""
+
+    KIN_FIELDS = ("T_tool", "T_links", "jacobian", "twist", "dtwist", "dtwist_lin", "dtwist_nonlin", "ddtwist",
+                  "ddtwist_lin", "ddtwist_nonlin", "torque")
+
+    def __init__(self, desc: ChainDesc, fast: bool = False):
+        self._l = lib(fast)
+        cdesc, keep = to_ctypes(desc)
+        self._h = self._l.lib.oracle_chain_create(ctypes.byref(cdesc))
+        if not self._h:
+            raise ValueError("oracle_chain_create failed")
+        del keep
+        self.nJ, self.nL, self.n_in = desc.n_joints, desc.n_joints + 1, desc.n_inputs
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.lib.oracle_chain_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def max_threads() -> int:
+        return int(lib().lib.oracle_max_threads())
+
+    def nominal_parameters(self) -> np.ndarray:
+        out = np.zeros(10 * self.nJ)
+        self._l.lib.oracle_nominal_parameters(self._h, _ptr(out))
+        return out
+
+    def kinematics(self, q, dq=None, ddq=None, dddq=None, want=KIN_FIELDS, nthreads=1):
+        q, dq, ddq, dddq = (_c(x, self.n_in) for x in (q, dq, ddq, dddq))
+        n = q.shape[1]
+        rows = {"T_tool": 12, "T_links": 12 * self.nL, "jacobian": 6 * self.n_in, "torque": self.n_in}
+        out = {k: (np.zeros((rows.get(k, 6 * self.nL), n)) if k in want else None) for k in self.KIN_FIELDS}
+        self._l.lib.oracle_kinematics_batch(self._h, n, n, _ptr(q), _ptr(dq), _ptr(ddq), _ptr(dddq), n,
+                                            *[_ptr(out[k]) for k in self.KIN_FIELDS], nthreads)
+        return {k: v for k, v in out.items() if v is not None}
+
+    def regressor_torque(self, q, dq, ddq, nthreads=1, store=True):
+        q, dq, ddq = (_c(x, self.n_in) for x in (q, dq, ddq))
+        n = q.shape[1]
+        phi = np.zeros((10 * self.nJ * self.n_in, n)) if store else None
+        tau = np.zeros((self.n_in, n)) if store else None
+        self._l.lib.oracle_regressor_torque_batch(self._h, n, n, _ptr(q), _ptr(dq), _ptr(ddq), n, _ptr(phi), _ptr(tau), nthreads)
+        return phi, tau
+
+    def inertia(self, q, nthreads=1):
+        q = _c(q, self.n_in)
+        n = q.shape[1]
+        M = np.zeros((self.n_in * self.n_in, n))
+        self._l.lib.oracle_inertia_batch(self._h, n, n, _ptr(q), n, _ptr(M), nthreads)
+        return M
+
+    def gram(self, q, dq, ddq, tau_meas=None):
+        q, dq, ddq, tau_meas = (_c(x, self.n_in) for x in (q, dq, ddq, tau_meas))
+        n = q.shape[1]
+        P = 10 * self.nJ
+        G, b, tt = np.zeros((P, P)), np.zeros(P), np.zeros(1)
+        self._l.lib.oracle_regressor_gram(self._h, n, n, _ptr(q), _ptr(dq), _ptr(ddq), _ptr(tau_meas), _ptr(G), _ptr(b), _ptr(tt))
+        return G, b, float(tt[0])  # G is symmetric, so column-major == row-major
