@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the rosdyn::Chain hot path on B200 (BASELINE.json metric:
+"6-DOF regressor+torque samples/sec (fp64)").
+
+One step = one pass of the hot path over one batch of synthetic (q,Dq,DDq) samples of the UR10-like 6-DOF chain
+(C6): getRegressor + getJointTorque for every sample.
+
+  --workload materialise : Phi (6x70, 420 SoA planes) + tau (6 planes) written to HBM        (HBM roofline)
+  --workload gram        : Phi and tau consumed in-kernel by the normal equations Phi^T Phi / Phi^T tau
+                           (FP64 DMMA roofline); N>1 adds one NCCL all-reduce of the (70^2+70+1) partials per step
+
+`value`  : device-resident inputs, CUDA-event timed, max over ranks.
+`e2e`    : the same metric through the C-ABI host-buffer entry point (pinned host inputs, H2D/D2H inside the timed region).
+`--impl reference` : the CPU restatement of the reference (oracle/, kind "port") on all host threads.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "6-DOF regressor+torque samples/sec (fp64)"
+UNIT = "samples/s"
+SEED = 0x5EED0000 + 1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("RDB_BENCH_WORKLOAD", "gram"), choices=["materialise", "gram"])
+    ap.add_argument("--chain", default="c6")
+    ap.add_argument("--samples", type=int, default=0, help="samples per step per GPU (0 = workload default)")
+    ap.add_argument("--e2e-samples", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target length of the bounded CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons during the timed region (NVML; nvidia-smi fallback)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                if self._nvml:
+                    p = self._nvml
+                    self.samples.append(float(p.nvmlDeviceGetClockInfo(self._h, p.NVML_CLOCK_SM)))
+                    r = p.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(p, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else p.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    table = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                             "hw_power_brake_slowdown": 0x80}
+                    for k, bit in table.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append(float(out[0]))
+                    self.max_mhz = float(out[1])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_run(chain_name: str, n: int, threads: int, reps: int = 1):
+    """getJointTorque + getRegressor per sample with the CPU restatement (oracle), all samples resident in host memory."""
+    from oracle.oracle import OracleChain, fill_uniform
+    from rosdyn_b200 import fixtures
+    d = fixtures.by_name(chain_name)
+    oc = OracleChain(d)
+    q, dq, ddq = (fill_uniform(d.n_inputs, n, SEED, s) for s in range(3))
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        oc.regressor_torque(q, dq, ddq, nthreads=threads, store=False)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return n / best, best
+
+
+def cpu_baseline(chain_name: str, seconds: float):
+    from oracle.oracle import OracleChain
+    threads = OracleChain.max_threads()
+    rate, _ = cpu_run(chain_name, 20000 * max(1, threads // 4), threads)       # calibration
+    n = int(max(50_000, min(rate * seconds, 50_000_000)))
+    rate, dt = cpu_run(chain_name, n, threads)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} samples of the same workload (getJointTorque + getRegressor per sample, oracle/rosdyn_oracle.c, "
+                      f"OpenMP {threads} threads, {dt:.1f} s)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (restatement, kind 'port'; the Eigen/ROS original cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import OracleChain
+    threads = OracleChain.max_threads()
+    rate, _ = cpu_run(args.chain, 20000 * max(1, threads // 4), threads)
+    n = int(max(20_000, min(rate * 4.0, 20_000_000)))                           # ~4 s per step
+    from oracle.oracle import fill_uniform
+    from rosdyn_b200 import fixtures
+    d = fixtures.by_name(args.chain)
+    oc = OracleChain(d)
+    q, dq, ddq = (fill_uniform(d.n_inputs, n, SEED, s) for s in range(3))
+    for _ in range(min(args.warmup, 1)):
+        oc.regressor_torque(q, dq, ddq, nthreads=threads, store=False)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        oc.regressor_torque(q, dq, ddq, nthreads=threads, store=False)
+    dt = time.perf_counter() - t
+    v = n * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"{args.chain}: getJointTorque + getRegressor per sample on the host CPU, {n} samples/step",
+                                        "chain": args.chain, "samples_per_step": n},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} samples/step x {args.steps} steps, oracle/rosdyn_oracle.c (plain-C restatement of primitives_impl.h), OpenMP"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rosdyn_b200 import fixtures
+    from rosdyn_b200.chain import Chain, fill_uniform, fp64_peak, kernel_launch_count
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    d = fixtures.by_name(args.chain)
+    ch = Chain(d)
+    n_in, P = d.n_inputs, 10 * d.n_joints
+    gram = args.workload == "gram"
+    S = args.samples or (8_000_000 if gram else 4_000_000)        # per GPU per step; inputs (and outputs) >> 126 MB L2
+    # weak scaling: every rank owns its own shard of S samples (disjoint sample indices via the seed offset)
+    q, dq, ddq = (fill_uniform(n_in, S, SEED + 1000003 * rank, s, device=dev) for s in range(3))
+    if gram:
+        G = torch.zeros((P, P), dtype=torch.float64, device=dev)
+        b = torch.zeros((P,), dtype=torch.float64, device=dev)
+        tt = torch.zeros((1,), dtype=torch.float64, device=dev)
+        flat = torch.zeros((P * P + P + 1,), dtype=torch.float64, device=dev)
+    else:
+        phi = torch.empty((P * n_in, S), dtype=torch.float64, device=dev)
+        tau = torch.empty((n_in, S), dtype=torch.float64, device=dev)
+
+    import ctypes
+    from rosdyn_b200._lib import CSamples, check, load
+    lib = load()
+    smp = CSamples(S, S, q.data_ptr(), dq.data_ptr(), ddq.data_ptr(), None)
+
+    def step():
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if gram:
+            check(lib.rdb_regressor_gram_batch(ch._h, ctypes.byref(smp), None, G.data_ptr(), b.data_ptr(), tt.data_ptr(), 0, st))
+            if world > 1:   # the one exchange step of the path: sum the small normal-equation partials over NVLink
+                flat[:P * P].copy_(G.reshape(-1))
+                flat[P * P:P * P + P].copy_(b)
+                flat[P * P + P:].copy_(tt)
+                dist.all_reduce(flat)
+        else:
+            check(lib.rdb_regressor_batch(ch._h, ctypes.byref(smp), phi.data_ptr(), tau.data_ptr(), S, st))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    l0 = kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = kernel_launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    value = world * S * args.steps / (ms * 1e-3)
+
+    # ------------------------------------------------------------------ e2e through the host-buffer C-ABI entry
+    e2e = None
+    if not args.no_e2e:
+        Se = args.e2e_samples or (4_000_000 if gram else 500_000)
+        hq, hdq, hddq = (torch.empty((n_in, Se), dtype=torch.float64).pin_memory() for _ in range(3))
+        for k, h in enumerate((hq, hdq, hddq)):
+            lib.rdb_fill_uniform_host(h.data_ptr(), n_in, Se, Se, SEED + 1000003 * rank, k)
+        hs = CSamples(Se, Se, hq.data_ptr(), hdq.data_ptr(), hddq.data_ptr(), None)
+        if gram:
+            hG = torch.empty((P, P), dtype=torch.float64).pin_memory()
+            hb = torch.empty((P,), dtype=torch.float64).pin_memory()
+            ht = torch.empty((1,), dtype=torch.float64).pin_memory()
+            hflat = torch.empty((P * P + P + 1,), dtype=torch.float64)
+
+            def e2e_step():
+                check(lib.rdb_regressor_gram_batch_host(ch._h, ctypes.byref(hs), None, hG.data_ptr(), hb.data_ptr(), ht.data_ptr(), 0))
+                if world > 1:
+                    hflat[:P * P] = hG.reshape(-1)
+                    hflat[P * P:P * P + P] = hb
+                    hflat[P * P + P:] = ht
+                    f = hflat.to(dev)
+                    dist.all_reduce(f)
+                    f.cpu()
+            h2d, d2h = 3 * n_in * Se * 8, (P * P + P + 1) * 8
+        else:
+            hphi = torch.empty((P * n_in, Se), dtype=torch.float64).pin_memory()
+            htau = torch.empty((n_in, Se), dtype=torch.float64).pin_memory()
+
+            def e2e_step():
+                check(lib.rdb_regressor_batch_host(ch._h, ctypes.byref(hs), hphi.data_ptr(), htau.data_ptr(), Se))
+            h2d, d2h = 3 * n_in * Se * 8, (P * n_in + n_in) * Se * 8
+        for _ in range(2):
+            e2e_step()
+        ke = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * Se * ke / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "samples_per_step_per_gpu": Se, "steps": ke,
+               "api": "rdb_regressor_gram_batch_host" if gram else "rdb_regressor_batch_host"}
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    peaks, src = measured_peaks()
+    if gram:
+        # algorithmic FLOPs per sample, BLAS SYRK+GEMV convention: n_act*P*(P+1) + 2*n_act*P
+        flop = n_in * P * (P + 1) + 2 * n_in * P
+        peak = None
+        if rank == 0:
+            peak = max(fp64_peak("dmma", 3), fp64_peak("dfma", 3))
+        ach = S * flop / (ms * 1e-3 / args.steps) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None, "traffic": None,
+                "peak_source": "own FP64 micro-benchmark on this GPU (max of DMMA m8n8k4 and DFMA); MEASURED_PEAKS.json has no FP64 figure",
+                "flop_per_sample": flop, "kernel": "regressor+gram step (all kernels of the step)"}
+    else:
+        bytes_per_sample = 8 * (3 * n_in + P * n_in + n_in)          # 3552 B for C6
+        ach = S * bytes_per_sample / (ms * 1e-3 / args.steps) / 1e9
+        peak = float(peaks["hbm_gbs"])
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})", "bytes_per_sample": bytes_per_sample, "kernel": "dyn_kernel<7,3> (regressor+torque)"}
+
+    if rank == 0:
+        cpu = None if args.no_cpu_baseline else cpu_baseline(args.chain, args.cpu_seconds)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": (f"{d.name}: getRegressor (6x70) + getJointTorque per sample, "
+                                    + ("fused into Phi^T Phi / Phi^T tau normal equations" if gram else "materialised as 426 SoA planes in HBM")),
+                       "chain": d.name, "samples_per_step_per_gpu": S, "mode": args.workload,
+                       "l2": "inputs (and outputs) per step are far larger than the 126 MB L2; no flush needed",
+                       "parallelism": f"{world} x independent sample shards" + (" + NCCL all-reduce of the partials" if gram and world > 1 else "")},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,94 @@
+"""ctypes binding of the C-ABI (include/rosdyn_b200.h).  Loads rosdyn_b200/librosdyn_b200.so and fails loudly
+when it is missing: the product has no CPU / eager fallback."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .descriptor import CChainDesc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librosdyn_b200.so")
+
+_dp = ctypes.c_void_p  # device or host pointer to double
+i32, i64, u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
+
+
+class CSamples(ctypes.Structure):
+    _fields_ = [("n", i64), ("ld", i64), ("q", _dp), ("dq", _dp), ("ddq", _dp), ("dddq", _dp)]
+
+
+KIN_FIELDS = ("T_tool", "T_links", "jacobian", "twist", "dtwist", "dtwist_lin", "dtwist_nonlin", "ddtwist", "ddtwist_lin",
+              "ddtwist_nonlin", "torque")
+
+
+class CKinematicsOut(ctypes.Structure):
+    _fields_ = [("ld", i64)] + [(k, _dp) for k in KIN_FIELDS]
+
+
+# every symbol include/rosdyn_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "rdb_abi_version": (i32, []),
+    "rdb_last_error": (ctypes.c_char_p, []),
+    "rdb_status_string": (ctypes.c_char_p, [i32]),
+    "rdb_device_count": (i32, []),
+    "rdb_kernel_launch_count": (u64, []),
+    "rdb_chain_create": (i32, [ctypes.POINTER(CChainDesc), ctypes.POINTER(ctypes.c_void_p)]),
+    "rdb_chain_destroy": (None, [ctypes.c_void_p]),
+    "rdb_chain_set_input_joints": (i32, [ctypes.c_void_p, i32, ctypes.POINTER(i32)]),
+    "rdb_chain_joints_number": (i32, [ctypes.c_void_p]),
+    "rdb_chain_links_number": (i32, [ctypes.c_void_p]),
+    "rdb_chain_active_joints_number": (i32, [ctypes.c_void_p]),
+    "rdb_chain_gravity": (i32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "rdb_chain_nominal_parameters": (i32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "rdb_kinematics_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(CKinematicsOut), ctypes.c_void_p]),
+    "rdb_torque_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, ctypes.c_void_p]),
+    "rdb_regressor_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, i64, ctypes.c_void_p]),
+    "rdb_inertia_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, ctypes.c_void_p]),
+    "rdb_regressor_gram_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, _dp, _dp, i32, ctypes.c_void_p]),
+    "rdb_kinematics_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(CKinematicsOut)]),
+    "rdb_torque_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64]),
+    "rdb_regressor_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, i64]),
+    "rdb_inertia_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64]),
+    "rdb_regressor_gram_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, _dp, _dp, i32]),
+    "rdb_fill_uniform": (i32, [_dp, i32, i64, i64, u64, i32, ctypes.c_void_p]),
+    "rdb_fill_uniform_host": (None, [_dp, i32, i64, i64, u64, i32]),
+    "rdb_fp64_peak": (i32, [i32, i32, ctypes.POINTER(ctypes.c_double)]),
+}
+
+RDB_OK, RDB_ERR_INVALID_ARG, RDB_ERR_DIM_MISMATCH, RDB_ERR_CUDA, RDB_ERR_NO_DEVICE, RDB_ERR_NOT_FOUND, RDB_ERR_ALLOC = range(7)
+
+_lib = None
+
+
+class RosdynB200Error(RuntimeError):
+    def __init__(self, status: int, text: str):
+        super().__init__(f"rosdyn_b200 status {status}: {text}")
+        self.status = status
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree C-ABI library and bind every declared symbol."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing - build it with `python -m rosdyn_b200.build` "
+                              "(rosdyn_b200 has no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int) -> None:
+    if status == RDB_OK:
+        return
+    lib = load()
+    msg = lib.rdb_last_error().decode() or lib.rdb_status_string(status).decode()
+    if status == RDB_ERR_DIM_MISMATCH:
+        # Chain::getRegressor throws std::invalid_argument("Input data dimensions mismatch") (primitives_impl.h:1299-1309)
+        raise ValueError(msg)
+    raise RosdynB200Error(status, msg)

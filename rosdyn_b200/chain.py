@@ -1,0 +1,374 @@
+"""Host-side mirror of `rosdyn::Chain` over the C-ABI (reference: rosdyn_core/include/rosdyn_core/primitives.h:235-555).
+
+Same method names and argument meaning as the reference; every method is ALSO its batched sibling:
+
+* 1-D joint vectors (length n_act)          -> one sample, results shaped like the reference's Eigen objects;
+* 2-D SoA arrays ``x[joint][N]`` (fp64)     -> N samples, results carry a trailing sample axis.
+
+torch CUDA tensors go through the device entry points on torch's current stream (asynchronous, results are
+torch CUDA tensors); numpy arrays go through the ``*_host`` entry points (copies + sync inside, results numpy).
+torch is used for device memory and streams only.  There is no CPU fallback: constructing a Chain without the
+built library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import CKinematicsOut, CSamples, KIN_FIELDS, check
+from .descriptor import ChainDesc, to_ctypes
+
+try:  # torch is plumbing (device buffers, streams); the host (numpy) path works without it
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _ndim(x) -> int:
+    return x.ndim if hasattr(x, "ndim") else np.ndim(x)
+
+
+def _shape(x):
+    return x.shape if hasattr(x, "shape") else np.shape(x)
+
+
+def _is_torch(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class Chain:
+    """Batched B200 drop-in for rosdyn::Chain (hot path only: kinematics, twists, RNEA, regressor, inertia)."""
+
+    def __init__(self, desc: ChainDesc):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        self.desc = desc
+        cdesc, keep = to_ctypes(desc)
+        check(self._lib.rdb_chain_create(ctypes.byref(cdesc), ctypes.byref(self._h)))
+        del keep
+        self.nJ = self._lib.rdb_chain_joints_number(self._h)
+        self.nL = self._lib.rdb_chain_links_number(self._h)
+        self.n_in = self._lib.rdb_chain_active_joints_number(self._h)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.rdb_chain_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------ metadata (primitives.h:364-447)
+    def getJointsNumber(self) -> int:
+        return self.nJ
+
+    def getLinksNumber(self) -> int:
+        return self.nL
+
+    def getActiveJointsNumber(self) -> int:
+        return self.n_in
+
+    def getLinksName(self):
+        return [l.name for l in self.desc.links]
+
+    def getMoveableJointNames(self):
+        return [j.name for j in self.desc.joints if j.type != 0]
+
+    def getActiveJointsName(self):
+        names = [None] * self.n_in
+        for j in self.desc.joints:
+            if j.input_index >= 0:
+                names[j.input_index] = j.name
+        return names
+
+    def getGravity(self) -> np.ndarray:
+        g = (ctypes.c_double * 3)()
+        check(self._lib.rdb_chain_gravity(self._h, g))
+        return np.array(g[:])
+
+    def setInputJointsName(self, names: Sequence[str]) -> bool:
+        """Chain::setInputJointsName (primitives_impl.h:705-742); False when a name is not in the chain."""
+        idx = {j.name: k for k, j in enumerate(self.desc.joints)}
+        sel = (ctypes.c_int32 * max(len(names), 1))(*[idx.get(n, -1) for n in names])
+        check(self._lib.rdb_chain_set_input_joints(self._h, len(names), sel))
+        ok = self.desc.set_input_joints(names)
+        self.n_in = len(names)
+        return ok
+
+    def getNominalParameters(self) -> np.ndarray:
+        out = (ctypes.c_double * (10 * self.nJ))()
+        check(self._lib.rdb_chain_nominal_parameters(self._h, out))
+        return np.array(out[:])
+
+    # ------------------------------------------------------------------ marshalling
+    def _prep(self, arrays):
+        """Returns (device?, single?, n, list of 2-D arrays or None)."""
+        first = next(a for a in arrays if a is not None)
+        dev = _is_torch(first) and first.is_cuda
+        single = _ndim(first) == 1
+        outs = []
+        n = None
+        for a in arrays:
+            if a is None:
+                outs.append(None)
+                continue
+            if _is_torch(a):
+                if a.is_cuda != dev:
+                    raise ValueError("all inputs must live on the same side (torch CUDA or host)")
+                a = a.to(torch.float64)
+                if a.ndim == 1:
+                    a = a.reshape(-1, 1)
+                if a.stride(-1) != 1:
+                    a = a.contiguous()
+                if not dev:
+                    a = a.numpy()
+            else:
+                a = np.asarray(a, dtype=np.float64)
+                if a.ndim == 1:
+                    a = a.reshape(-1, 1)
+                if a.strides[-1] != 8:
+                    a = np.ascontiguousarray(a)
+            if a.ndim != 2 or a.shape[0] != self.n_in:
+                # the reference only checks sizes in getRegressor (primitives_impl.h:1299-1309); here every getter does
+                raise ValueError("Input data dimensions mismatch")
+            if n is None:
+                n = a.shape[1]
+            elif a.shape[1] != n:
+                raise ValueError("Input data dimensions mismatch")
+            outs.append(a)
+        lds = {(_ld(a)) for a in outs if a is not None}
+        if len(lds) > 1:  # the ABI takes one plane stride for all joint arrays
+            outs = [None if a is None else (a.contiguous() if _is_torch(a) else np.ascontiguousarray(a)) for a in outs]
+        return dev, single, n, outs
+
+    def _samples(self, n, arrs) -> CSamples:
+        s = CSamples()
+        s.n = n
+        first = next(a for a in arrs if a is not None)
+        s.ld = _ld(first)
+        s.q, s.dq, s.ddq, s.dddq = (_ptr(a) for a in arrs)
+        return s
+
+    def _alloc(self, dev: bool, planes: int, n: int, like):
+        if dev:
+            return torch.empty((planes, n), dtype=torch.float64, device=like.device)
+        return np.empty((planes, n), dtype=np.float64)
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ------------------------------------------------------------------ kinematics
+    def kinematics(self, q, Dq=None, DDq=None, DDDq=None, want: Sequence[str] = ("T_tool",)):
+        """One pass producing any subset of rdb_kinematics_out; returns {name: planes[rows][N]} (raw plane layout)."""
+        dev, single, n, arrs = self._prep([q, Dq, DDq, DDDq])
+        rows = {"T_tool": 12, "T_links": 12 * self.nL, "jacobian": 6 * self.n_in, "torque": self.n_in}
+        out = CKinematicsOut()
+        out.ld = max(n, 1)
+        res = {}
+        for k in KIN_FIELDS:
+            if k in want:
+                res[k] = self._alloc(dev, rows.get(k, 6 * self.nL), n, arrs[0])
+                setattr(out, k, _ptr(res[k]))
+        s = self._samples(n, arrs)
+        if dev:
+            check(self._lib.rdb_kinematics_batch(self._h, ctypes.byref(s), ctypes.byref(out), self._stream()))
+        else:
+            check(self._lib.rdb_kinematics_batch_host(self._h, ctypes.byref(s), ctypes.byref(out)))
+        return res
+
+    def _kin1(self, name, shape, q, Dq=None, DDq=None, DDDq=None):
+        single = (_ndim(q) == 1)
+        r = self.kinematics(q, Dq, DDq, DDDq, want=(name,))[name]
+        r = r.reshape(*shape, r.shape[-1])
+        return r[..., 0] if single else r
+
+    def getTransformation(self, q):
+        """Chain::getTransformation (PI.h:884): T_bt as 3x4 [R|p] (x N); a single sample returns the 4x4 Affine3d image."""
+        r = self._kin1("T_tool", (3, 4), q)
+        return _affine(r) if _ndim(q) == 1 else r
+
+    computeTransformations = getTransformation  # name used by BASELINE.json's north_star (no such reference symbol)
+
+    def getTransformations(self, q):
+        """Chain::getTransformations (PI.h:908): all links, [nL,3,4(,N)]."""
+        return self._kin1("T_links", (self.nL, 3, 4), q)
+
+    def getJacobian(self, q):
+        """Chain::getJacobian (PI.h:927): 6 x n_act (x N)."""
+        r = self._kin1("jacobian", (self.n_in, 6), q)
+        return _swap01(r)
+
+    def getTwist(self, q, Dq):
+        return self._kin1("twist", (self.nL, 6), q, Dq)
+
+    def getTwistTool(self, q, Dq):
+        return self.getTwist(q, Dq)[-1]
+
+    def getDTwist(self, q, Dq, DDq):
+        return self._kin1("dtwist", (self.nL, 6), q, Dq, DDq)
+
+    def getDTwistTool(self, q, Dq, DDq):
+        return self.getDTwist(q, Dq, DDq)[-1]
+
+    def getDTwistLinearPart(self, q, DDq):
+        return self._kin1("dtwist_lin", (self.nL, 6), q, None, DDq)
+
+    def getDTwistNonLinearPart(self, q, Dq):
+        return self._kin1("dtwist_nonlin", (self.nL, 6), q, Dq)
+
+    def getDDTwist(self, q, Dq, DDq, DDDq):
+        return self._kin1("ddtwist", (self.nL, 6), q, Dq, DDq, DDDq)
+
+    def getDDTwistTool(self, q, Dq, DDq, DDDq):
+        return self.getDDTwist(q, Dq, DDq, DDDq)[-1]
+
+    def getDDTwistLinearPart(self, q, DDDq):
+        return self._kin1("ddtwist_lin", (self.nL, 6), q, None, None, DDDq)
+
+    def getDDTwistNonLinearPart(self, q, Dq, DDq):
+        return self._kin1("ddtwist_nonlin", (self.nL, 6), q, Dq, DDq)
+
+    # ------------------------------------------------------------------ dynamics
+    def getJointTorque(self, q, Dq, DDq):
+        """Chain::getJointTorque(q,Dq,DDq) (PI.h:1277): n_act (x N)."""
+        dev, single, n, arrs = self._prep([q, Dq, DDq, None])
+        tau = self._alloc(dev, self.n_in, n, arrs[0])
+        s = self._samples(n, arrs)
+        if dev:
+            check(self._lib.rdb_torque_batch(self._h, ctypes.byref(s), _ptr(tau), max(n, 1), self._stream()))
+        else:
+            check(self._lib.rdb_torque_batch_host(self._h, ctypes.byref(s), _ptr(tau), max(n, 1)))
+        return tau[:, 0] if single else tau
+
+    def getJointTorqueNonLinearPart(self, q, Dq):
+        """PI.h:1285-1293: getJointTorque with DDq = 0."""
+        return self.getJointTorque(q, Dq, None)
+
+    def getRegressor(self, q, Dq, DDq, with_torque: bool = False):
+        """Chain::getRegressor (PI.h:1295): n_act x 10*nJ (x N).  with_torque also returns getJointTorque of the
+        same samples from the same pass."""
+        if Dq is None or DDq is None or tuple(_shape(q)) != tuple(_shape(Dq)) or tuple(_shape(Dq)) != tuple(_shape(DDq)):
+            raise ValueError("Input data dimensions mismatch")
+        dev, single, n, arrs = self._prep([q, Dq, DDq, None])
+        P = 10 * self.nJ
+        phi = self._alloc(dev, P * self.n_in, n, arrs[0])
+        tau = self._alloc(dev, self.n_in, n, arrs[0]) if with_torque else None
+        s = self._samples(n, arrs)
+        if dev:
+            check(self._lib.rdb_regressor_batch(self._h, ctypes.byref(s), _ptr(phi), _ptr(tau), max(n, 1), self._stream()))
+        else:
+            check(self._lib.rdb_regressor_batch_host(self._h, ctypes.byref(s), _ptr(phi), _ptr(tau), max(n, 1)))
+        r = _swap01(phi.reshape(P, self.n_in, n))
+        if single:
+            r = r[..., 0]
+            tau = tau[:, 0] if tau is not None else None
+        return (r, tau) if with_torque else r
+
+    def getJointInertia(self, q):
+        """Chain::getJointInertia (PI.h:1357): n_act x n_act (x N)."""
+        dev, single, n, arrs = self._prep([q, None, None, None])
+        M = self._alloc(dev, self.n_in * self.n_in, n, arrs[0])
+        s = self._samples(n, arrs)
+        if dev:
+            check(self._lib.rdb_inertia_batch(self._h, ctypes.byref(s), _ptr(M), max(n, 1), self._stream()))
+        else:
+            check(self._lib.rdb_inertia_batch_host(self._h, ctypes.byref(s), _ptr(M), max(n, 1)))
+        r = _swap01(M.reshape(self.n_in, self.n_in, n))
+        return r[..., 0] if single else r
+
+    def regressorGram(self, q, Dq, DDq, tau_meas=None, out=None):
+        """Fused getRegressor -> normal equations: returns (G[P,P], b[P], tau_sq[1]) with
+        G = sum Phi^T Phi, b = sum Phi^T tau, tau_sq = sum tau^T tau; tau = tau_meas or getJointTorque.
+        `out=(G,b,tau_sq)` accumulates into existing arrays (chunked / multi-pass use)."""
+        if Dq is None or DDq is None:
+            raise ValueError("Input data dimensions mismatch")
+        dev, single, n, arrs = self._prep([q, Dq, DDq, None])
+        tau_arr = None
+        if tau_meas is not None:
+            _, _, nt, (tau_arr,) = self._prep([tau_meas])
+            if nt != n or _ld(tau_arr) != _ld(arrs[0]):
+                tau_arr = tau_arr.contiguous() if _is_torch(tau_arr) else np.ascontiguousarray(tau_arr)
+                if _ld(tau_arr) != _ld(arrs[0]):
+                    arrs = [None if a is None else (a.contiguous() if _is_torch(a) else np.ascontiguousarray(a)) for a in arrs]
+        P = 10 * self.nJ
+        acc = out is not None
+        if acc:
+            G, b, tt = out
+        elif dev:
+            G = torch.empty((P, P), dtype=torch.float64, device=arrs[0].device)
+            b = torch.empty((P,), dtype=torch.float64, device=arrs[0].device)
+            tt = torch.empty((1,), dtype=torch.float64, device=arrs[0].device)
+        else:
+            G, b, tt = np.empty((P, P)), np.empty((P,)), np.empty((1,))
+        s = self._samples(n, arrs)
+        if dev:
+            check(self._lib.rdb_regressor_gram_batch(self._h, ctypes.byref(s), _ptr(tau_arr), _ptr(G), _ptr(b), _ptr(tt), int(acc), self._stream()))
+        else:
+            check(self._lib.rdb_regressor_gram_batch_host(self._h, ctypes.byref(s), _ptr(tau_arr), _ptr(G), _ptr(b), _ptr(tt), int(acc)))
+        return G, b, tt
+
+
+# ---------------------------------------------------------------------- helpers
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_torch(a):
+        return ctypes.c_void_p(a.data_ptr())
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _ld(a) -> int:
+    if _is_torch(a):
+        return int(a.stride(0)) if a.shape[0] > 1 else max(int(a.shape[1]), 1)
+    return int(a.strides[0] // 8) if a.shape[0] > 1 else max(int(a.shape[1]), 1)
+
+
+def _swap01(a):
+    return a.transpose(0, 1) if _is_torch(a) else np.swapaxes(a, 0, 1)
+
+
+def _affine(r34):
+    if _is_torch(r34):
+        T = torch.eye(4, dtype=torch.float64, device=r34.device)
+        T[:3, :] = r34
+        return T
+    T = np.eye(4)
+    T[:3, :] = r34
+    return T
+
+
+def fill_uniform(n_planes: int, n: int, seed: int, stream_id: int, device=None):
+    """U(-1,1) synthetic joint samples x[plane][n] (rdb_fill_uniform): torch CUDA tensor, or numpy when device is None."""
+    lib = _lib.load()
+    if device is None:
+        x = np.empty((n_planes, n))
+        lib.rdb_fill_uniform_host(_ptr(x), n_planes, n, max(n, 1), seed, stream_id)
+        return x
+    x = torch.empty((n_planes, n), dtype=torch.float64, device=device)
+    check(lib.rdb_fill_uniform(_ptr(x), n_planes, n, max(n, 1), seed, stream_id, Chain._stream()))
+    return x
+
+
+def fp64_peak(kind: str = "dmma", reps: int = 5) -> float:
+    """Own FP64 roofline denominator in TFLOP/s: 'dfma' (vector pipe) or 'dmma' (mma.sync m8n8k4 f64)."""
+    v = ctypes.c_double()
+    check(_lib.load().rdb_fp64_peak(0 if kind == "dfma" else 1, reps, ctypes.byref(v)))
+    return float(v.value)
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.load().rdb_kernel_launch_count())
+
+
+def createChain(desc: ChainDesc, gravity: Optional[Sequence[float]] = None) -> Optional[Chain]:
+    """rosdyn::createChain (primitives_impl.h:1518-1527): returns None instead of raising when the model is bad."""
+    if gravity is not None:
+        desc.gravity = tuple(gravity)
+    try:
+        return Chain(desc)
+    except _lib.RosdynB200Error as e:
+        if e.status == _lib.RDB_ERR_INVALID_ARG:
+            return None
+        raise

@@ -1,0 +1,616 @@
+// capi.cu -- implementation of the C-ABI declared in include/rosdyn_b200.h.
+// Host-side model build (the cold path of Joint::fromUrdf / Link::fromUrdf / Chain::init, reference
+// primitives_impl.h:50-83, 288-319, 399-417, 580-742) + argument checking + launches.  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+
+namespace rdb
+{
+std::atomic<uint64_t> g_launches{0};
+static thread_local std::string t_err;
+
+static rdb_status fail(rdb_status s, const std::string& what)
+{
+  t_err = what;
+  return s;
+}
+static rdb_status cuda_fail(cudaError_t e, const char* where)
+{
+  return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? RDB_ERR_NO_DEVICE : RDB_ERR_CUDA,
+              std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define RDB_CUDA(call)                                   \
+  do                                                     \
+  {                                                      \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+static void mat3_mul(const double* a, const double* b, double* c)
+{
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+    {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += a[3 * i + k] * b[3 * k + j];
+      c[3 * i + j] = s;
+    }
+}
+static void skew(const double* v, double* m)
+{
+  m[0] = 0; m[1] = -v[2]; m[2] = v[1];
+  m[3] = v[2]; m[4] = 0; m[5] = -v[0];
+  m[6] = -v[1]; m[7] = v[0]; m[8] = 0;
+}
+
+// Joint::fromUrdf (primitives_impl.h:54-83) + Link::fromUrdf (288-319) + getNominalParameters (399-417)
+static rdb_status build_model(const rdb_chain_desc* d, ChainHost* ch)
+{
+  ChainDev<RDB_MAX_JOINTS>& H = ch->host;
+  std::memset(&H, 0, sizeof(H));
+  H.nj = d->n_joints;
+  H.n_in = d->n_inputs;
+  for (int k = 0; k < 3; k++) H.g[k] = d->gravity[k];
+  for (int j = 0; j < d->n_joints; j++)
+  {
+    const rdb_joint_desc& s = d->joints[j];
+    JointDev& o = H.joint[j];
+    if (s.type != RDB_JOINT_FIXED && s.type != RDB_JOINT_REVOLUTE && s.type != RDB_JOINT_PRISMATIC)
+      return fail(RDB_ERR_INVALID_ARG, "joint type must be RDB_JOINT_FIXED/REVOLUTE/PRISMATIC");
+    if (s.input_index < -1 || s.input_index >= d->n_inputs) return fail(RDB_ERR_INVALID_ARG, "joint input_index out of range");
+    o.type = s.type;
+    o.in = s.input_index;
+    const double n = std::sqrt(s.axis[0] * s.axis[0] + s.axis[1] * s.axis[1] + s.axis[2] * s.axis[2]);
+    for (int k = 0; k < 3; k++) o.ax[k] = n > 0 ? s.axis[k] / n : s.axis[k];
+    double K[9], K2[9];
+    skew(o.ax, K);
+    mat3_mul(K, K, K2);
+    std::memcpy(o.A, s.rot, sizeof(o.A));
+    mat3_mul(s.rot, K, o.B);
+    mat3_mul(s.rot, K2, o.C);
+    for (int r = 0; r < 3; r++)
+    {
+      o.t[r] = s.xyz[r];
+      o.axp[r] = s.rot[3 * r] * o.ax[0] + s.rot[3 * r + 1] * o.ax[1] + s.rot[3 * r + 2] * o.ax[2];
+    }
+  }
+  for (int l = 0; l < d->n_joints; l++)
+  {
+    const rdb_link_desc& s = d->links[l + 1];
+    double I[9] = {s.inertia[0], s.inertia[1], s.inertia[2], s.inertia[1], s.inertia[3], s.inertia[4], s.inertia[2], s.inertia[4], s.inertia[5]};
+    double Rt[9], t[9], Ir[9], cs[9], cst[9], cc[9];
+    for (int i = 0; i < 3; i++)
+      for (int k = 0; k < 3; k++) Rt[3 * i + k] = s.inertial_rot[3 * k + i];
+    mat3_mul(s.inertial_rot, I, t);
+    mat3_mul(t, Rt, Ir);
+    skew(s.cog, cs);
+    for (int i = 0; i < 3; i++)
+      for (int k = 0; k < 3; k++) cst[3 * i + k] = cs[3 * k + i];
+    mat3_mul(cs, cst, cc);
+    double I0[9];
+    for (int k = 0; k < 9; k++) I0[k] = Ir[k] + s.mass * cc[k];  // spacevect_algebra.h:238
+    double* P = H.link[l].pi;
+    P[0] = s.mass;
+    for (int k = 0; k < 3; k++) P[1 + k] = s.cog[k] * s.mass;
+    P[4] = I0[0]; P[5] = I0[1]; P[6] = I0[2];
+    P[7] = I0[4]; P[8] = I0[5]; P[9] = I0[8];
+    std::memcpy(ch->nominal + 10 * l, P, 10 * sizeof(double));
+  }
+  std::vector<int> fed(std::max(d->n_inputs, 1), 0);
+  for (int j = 0; j < d->n_joints; j++)
+    if (H.joint[j].in >= 0)
+    {
+      if (fed[H.joint[j].in]) return fail(RDB_ERR_INVALID_ARG, "two chain joints share one input index");
+      fed[H.joint[j].in] = 1;
+    }
+  ch->inputs_cover_all = true;
+  for (int i = 0; i < d->n_inputs; i++) ch->inputs_cover_all = ch->inputs_cover_all && fed[i];
+  return RDB_OK;
+}
+
+static rdb_status upload_model(ChainHost* ch)
+{
+  RDB_CUDA(cudaGetDevice(&ch->device));
+  if (!ch->dev) RDB_CUDA(cudaMalloc(&ch->dev, sizeof(ch->host)));
+  RDB_CUDA(cudaMemcpy(ch->dev, &ch->host, sizeof(ch->host), cudaMemcpyHostToDevice));
+  cudaDeviceGetAttribute(&ch->sm_count, cudaDevAttrMultiProcessorCount, ch->device);
+  return RDB_OK;
+}
+
+static rdb_status check_samples(const ChainHost* ch, const rdb_samples* in, bool need_q)
+{
+  if (!ch || !in) return fail(RDB_ERR_INVALID_ARG, "null chain or samples");
+  if (in->n < 0 || in->ld < in->n) return fail(RDB_ERR_INVALID_ARG, "samples: need 0 <= n <= ld");
+  if (need_q && !in->q && ch->host.n_in > 0) return fail(RDB_ERR_DIM_MISMATCH, "q is required");
+  return RDB_OK;
+}
+
+static SamplesDev to_dev(const rdb_samples* in) { return SamplesDev{in->n, in->ld, in->q, in->dq, in->ddq, in->dddq}; }
+
+static unsigned kin_mask(const rdb_kinematics_out* o)
+{
+  unsigned m = 0;
+  if (o->T_tool) m |= K_TTOOL;
+  if (o->T_links) m |= K_TLINKS;
+  if (o->jacobian) m |= K_JAC;
+  if (o->twist) m |= K_TWIST;
+  if (o->dtwist) m |= K_DTWIST;
+  if (o->dtwist_lin) m |= K_DTWIST_LIN;
+  if (o->dtwist_nonlin) m |= K_DTWIST_NONLIN;
+  if (o->ddtwist) m |= K_DDTWIST;
+  if (o->ddtwist_lin) m |= K_DDTWIST_LIN;
+  if (o->ddtwist_nonlin) m |= K_DDTWIST_NONLIN;
+  if (o->torque) m |= K_TORQUE;
+  return m;
+}
+
+// rows/columns of inputs that no chain joint feeds stay zero in the reference (S has a zero column there)
+static rdb_status prezero(const ChainHost* ch, double* p, int64_t planes, int64_t ld, int64_t n, cudaStream_t st)
+{
+  if (ch->inputs_cover_all || !p || n <= 0) return RDB_OK;
+  RDB_CUDA(cudaMemset2DAsync(p, ld * sizeof(double), 0, n * sizeof(double), planes, st));
+  return RDB_OK;
+}
+
+}  // namespace rdb
+
+using namespace rdb;
+
+struct rdb_chain : public rdb::ChainHost
+{
+};
+
+extern "C" {
+
+int32_t rdb_abi_version(void) { return RDB_ABI_VERSION; }
+const char* rdb_last_error(void) { return t_err.c_str(); }
+const char* rdb_status_string(rdb_status s)
+{
+  switch (s)
+  {
+    case RDB_OK: return "ok";
+    case RDB_ERR_INVALID_ARG: return "invalid argument";
+    case RDB_ERR_DIM_MISMATCH: return "Input data dimensions mismatch";
+    case RDB_ERR_CUDA: return "CUDA error";
+    case RDB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case RDB_ERR_NOT_FOUND: return "not found";
+    case RDB_ERR_ALLOC: return "allocation failed";
+  }
+  return "unknown status";
+}
+int32_t rdb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+uint64_t rdb_kernel_launch_count(void) { return g_launches.load(); }
+
+rdb_status rdb_chain_create(const rdb_chain_desc* desc, rdb_chain** out)
+{
+  if (!desc || !out) return fail(RDB_ERR_INVALID_ARG, "null descriptor or output");
+  *out = nullptr;
+  if (desc->n_joints < 0 || desc->n_joints > RDB_MAX_JOINTS) return fail(RDB_ERR_INVALID_ARG, "n_joints out of range");
+  if (desc->n_inputs < 0 || desc->n_inputs > RDB_MAX_JOINTS) return fail(RDB_ERR_INVALID_ARG, "n_inputs out of range");
+  if (desc->n_joints > 0 && !desc->joints) return fail(RDB_ERR_INVALID_ARG, "null joints");
+  if (!desc->links) return fail(RDB_ERR_INVALID_ARG, "null links");
+  rdb_chain* ch = new (std::nothrow) rdb_chain();
+  if (!ch) return fail(RDB_ERR_ALLOC, "out of host memory");
+  rdb_status s = build_model(desc, ch);
+  if (s == RDB_OK)
+  {
+    if (rdb_device_count() <= 0) s = fail(RDB_ERR_NO_DEVICE, "no CUDA device: rosdyn_b200 has no CPU fallback");
+    else s = upload_model(ch);
+  }
+  if (s != RDB_OK)
+  {
+    if (ch->dev) cudaFree(ch->dev);
+    delete ch;
+    return s;
+  }
+  *out = ch;
+  return RDB_OK;
+}
+
+void rdb_chain_destroy(rdb_chain* chain)
+{
+  if (!chain) return;
+  if (chain->dev) cudaFree(chain->dev);
+  if (chain->gram.partials) cudaFree(chain->gram.partials);
+  delete chain;
+}
+
+rdb_status rdb_chain_set_input_joints(rdb_chain* chain, int32_t n_inputs, const int32_t* chain_joint_of_input)
+{
+  if (!chain || n_inputs < 0 || n_inputs > RDB_MAX_JOINTS || (n_inputs > 0 && !chain_joint_of_input))
+    return fail(RDB_ERR_INVALID_ARG, "bad input-joint selection");
+  std::vector<int> in(chain->host.nj, -1);
+  bool all = true;
+  for (int i = 0; i < n_inputs; i++)
+  {
+    const int j = chain_joint_of_input[i];
+    if (j < 0 || j >= chain->host.nj)
+    {
+      all = false;  // "Joint named '%s' not found" (primitives_impl.h:734): the input keeps a zero column of S
+      continue;
+    }
+    if (in[j] >= 0) return fail(RDB_ERR_INVALID_ARG, "chain joint selected twice");
+    in[j] = i;
+  }
+  for (int j = 0; j < chain->host.nj; j++) chain->host.joint[j].in = in[j];
+  chain->host.n_in = n_inputs;
+  chain->inputs_cover_all = all;
+  return upload_model(chain);
+}
+
+int32_t rdb_chain_joints_number(const rdb_chain* chain) { return chain ? chain->host.nj : -1; }
+int32_t rdb_chain_links_number(const rdb_chain* chain) { return chain ? chain->host.nj + 1 : -1; }
+int32_t rdb_chain_active_joints_number(const rdb_chain* chain) { return chain ? chain->host.n_in : -1; }
+rdb_status rdb_chain_gravity(const rdb_chain* chain, double out[3])
+{
+  if (!chain || !out) return fail(RDB_ERR_INVALID_ARG, "null argument");
+  for (int k = 0; k < 3; k++) out[k] = chain->host.g[k];
+  return RDB_OK;
+}
+rdb_status rdb_chain_nominal_parameters(const rdb_chain* chain, double* out)
+{
+  if (!chain || !out) return fail(RDB_ERR_INVALID_ARG, "null argument");
+  std::memcpy(out, chain->nominal, sizeof(double) * 10 * chain->host.nj);
+  return RDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------- device entries
+rdb_status rdb_kinematics_batch(const rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  if (!out || out->ld < in->n) return fail(RDB_ERR_INVALID_ARG, "kinematics_out: need ld >= n");
+  const unsigned mask = kin_mask(out);
+  if (!mask || in->n == 0) return RDB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nL = chain->host.nj + 1, n_in = chain->host.n_in;
+  if ((s = prezero(chain, out->jacobian, 6 * n_in, out->ld, in->n, st)) != RDB_OK) return s;
+  if ((s = prezero(chain, out->torque, n_in, out->ld, in->n, st)) != RDB_OK) return s;
+  (void)nL;
+  KinOutDev o{out->ld,         out->T_tool,        out->T_links, out->jacobian,    out->twist,          out->dtwist,
+              out->dtwist_lin, out->dtwist_nonlin, out->ddtwist, out->ddtwist_lin, out->ddtwist_nonlin, out->torque};
+  RDB_CUDA(launch_kin(*chain, mask, to_dev(in), o, st));
+  return RDB_OK;
+}
+
+rdb_status rdb_torque_batch(const rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  if (!torque || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "torque: null or ld_out < n");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((s = prezero(chain, torque, chain->host.n_in, ld_out, in->n, st)) != RDB_OK) return s;
+  RDB_CUDA(launch_dyn(*chain, DYN_TORQUE_, to_dev(in), nullptr, torque, nullptr, ld_out, st));
+  return RDB_OK;
+}
+
+rdb_status rdb_regressor_batch(const rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, int64_t ld_out, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  // Chain::getRegressor throws std::invalid_argument("Input data dimensions mismatch") (primitives_impl.h:1299-1309)
+  if (!in->dq || !in->ddq) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (!phi || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "phi: null or ld_out < n");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_in = chain->host.n_in;
+  if ((s = prezero(chain, phi, (int64_t)10 * chain->host.nj * n_in, ld_out, in->n, st)) != RDB_OK) return s;
+  if ((s = prezero(chain, torque, n_in, ld_out, in->n, st)) != RDB_OK) return s;
+  RDB_CUDA(launch_dyn(*chain, torque ? (DYN_REGRESSOR_ | DYN_TORQUE_) : DYN_REGRESSOR_, to_dev(in), phi, torque, nullptr, ld_out, st));
+  return RDB_OK;
+}
+
+rdb_status rdb_inertia_batch(const rdb_chain* chain, const rdb_samples* in, double* inertia, int64_t ld_out, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  if (!inertia || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "inertia: null or ld_out < n");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_in = chain->host.n_in;
+  if ((s = prezero(chain, inertia, (int64_t)n_in * n_in, ld_out, in->n, st)) != RDB_OK) return s;
+  RDB_CUDA(launch_dyn(*chain, DYN_INERTIA_, to_dev(in), nullptr, nullptr, inertia, ld_out, st));
+  return RDB_OK;
+}
+
+rdb_status rdb_regressor_gram_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+                                    double* tau_sq, int32_t accumulate, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  if (!in->dq || !in->ddq) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (!gram || !rhs) return fail(RDB_ERR_INVALID_ARG, "gram / rhs must not be null");
+  RDB_CUDA(launch_gram(*const_cast<rdb_chain*>(chain), to_dev(in), tau_meas, gram, rhs, tau_sq, accumulate, (cudaStream_t)stream));
+  return RDB_OK;
+}
+
+rdb_status rdb_fill_uniform(double* x, int32_t n_planes, int64_t n, int64_t ld, uint64_t seed, int32_t stream_id, void* stream)
+{
+  if (!x || n_planes < 0 || n_planes > 64 || n < 0 || ld < n || stream_id < 0 || stream_id > 3)
+    return fail(RDB_ERR_INVALID_ARG, "fill_uniform: bad argument");
+  if (rdb_device_count() <= 0) return fail(RDB_ERR_NO_DEVICE, "no CUDA device");
+  RDB_CUDA(launch_fill_uniform(x, n_planes, n, ld, seed, stream_id, (cudaStream_t)stream));
+  return RDB_OK;
+}
+void rdb_fill_uniform_host(double* x, int32_t n_planes, int64_t n, int64_t ld, uint64_t seed, int32_t stream_id)
+{
+  fill_uniform_host(x, n_planes, n, ld, seed, stream_id);
+}
+
+rdb_status rdb_fp64_peak(int32_t kind, int32_t reps, double* tflops)
+{
+  if (!tflops || kind < 0 || kind > 1) return fail(RDB_ERR_INVALID_ARG, "fp64_peak: bad argument");
+  if (rdb_device_count() <= 0) return fail(RDB_ERR_NO_DEVICE, "no CUDA device");
+  RDB_CUDA(fp64_peak(kind, reps, tflops));
+  return RDB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------- host wrappers
+// Chunked, double-buffered: H2D of chunk k+1 and D2H of chunk k-1 overlap the kernel of chunk k when the
+// caller's buffers are pinned (cudaMemcpy2DAsync gathers each plane's slice).
+namespace rdb
+{
+struct Plane
+{
+  const double* h_in = nullptr;  // host source (inputs)
+  double* h_out = nullptr;       // host destination (outputs)
+  int64_t planes = 0;
+  int64_t ld = 0;  // host plane stride
+  double* d[2] = {nullptr, nullptr};
+};
+
+struct HostPipe
+{
+  cudaStream_t st[2] = {nullptr, nullptr};
+  std::vector<Plane*> all;
+  int64_t chunk = 0;
+  ~HostPipe()
+  {
+    for (Plane* p : all)
+      for (int k = 0; k < 2; k++)
+        if (p->d[k]) cudaFree(p->d[k]);
+    for (int k = 0; k < 2; k++)
+      if (st[k]) cudaStreamDestroy(st[k]);
+  }
+  rdb_status init(int64_t n, int64_t chunk_max, std::vector<Plane*> planes)
+  {
+    all = planes;
+    chunk = std::min<int64_t>(std::max<int64_t>(n, 1), chunk_max);
+    const int slots = n > chunk ? 2 : 1;
+    for (int k = 0; k < slots; k++) RDB_CUDA(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+    for (Plane* p : all)
+      if ((p->h_in || p->h_out) && p->planes > 0)
+        for (int k = 0; k < slots; k++) RDB_CUDA(cudaMalloc(&p->d[k], sizeof(double) * p->planes * chunk));
+    return RDB_OK;
+  }
+  rdb_status h2d(Plane& p, int slot, int64_t off, int64_t len)
+  {
+    if (!p.h_in || p.planes == 0) return RDB_OK;
+    RDB_CUDA(cudaMemcpy2DAsync(p.d[slot], chunk * sizeof(double), p.h_in + off, p.ld * sizeof(double), len * sizeof(double), p.planes,
+                               cudaMemcpyHostToDevice, st[slot]));
+    return RDB_OK;
+  }
+  rdb_status d2h(Plane& p, int slot, int64_t off, int64_t len)
+  {
+    if (!p.h_out || p.planes == 0) return RDB_OK;
+    RDB_CUDA(cudaMemcpy2DAsync(p.h_out + off, p.ld * sizeof(double), p.d[slot], chunk * sizeof(double), len * sizeof(double), p.planes,
+                               cudaMemcpyDeviceToHost, st[slot]));
+    return RDB_OK;
+  }
+  rdb_status finish()
+  {
+    for (int k = 0; k < 2; k++)
+      if (st[k]) RDB_CUDA(cudaStreamSynchronize(st[k]));
+    return RDB_OK;
+  }
+};
+
+struct HostIn
+{
+  Plane q, dq, ddq, dddq;
+  void bind(const rdb_samples* in, int n_in)
+  {
+    const double* src[4] = {in->q, in->dq, in->ddq, in->dddq};
+    Plane* dst[4] = {&q, &dq, &ddq, &dddq};
+    for (int k = 0; k < 4; k++)
+    {
+      dst[k]->h_in = src[k];
+      dst[k]->planes = src[k] ? n_in : 0;
+      dst[k]->ld = in->ld;
+    }
+  }
+  rdb_samples view(int slot, int64_t len, int64_t chunk) const
+  {
+    return rdb_samples{len, chunk, q.d[slot], dq.d[slot], ddq.d[slot], dddq.d[slot]};
+  }
+};
+}  // namespace rdb
+
+#define RDB_TRY(x)                    \
+  do                                  \
+  {                                   \
+    rdb_status s__ = (x);             \
+    if (s__ != RDB_OK) return s__;    \
+  } while (0)
+
+extern "C" {
+
+rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out)
+{
+  RDB_TRY(check_samples(chain, in, true));
+  if (!out || out->ld < in->n) return fail(RDB_ERR_INVALID_ARG, "kinematics_out: need ld >= n");
+  const int nL = chain->host.nj + 1, n_in = chain->host.n_in;
+  HostIn hi;
+  hi.bind(in, n_in);
+  double* const outs[11] = {out->T_tool,        out->T_links, out->jacobian,    out->twist,          out->dtwist, out->dtwist_lin,
+                            out->dtwist_nonlin, out->ddtwist, out->ddtwist_lin, out->ddtwist_nonlin, out->torque};
+  const int64_t rows[11] = {12, 12 * nL, 6 * n_in, 6 * nL, 6 * nL, 6 * nL, 6 * nL, 6 * nL, 6 * nL, 6 * nL, n_in};
+  Plane po[11];
+  std::vector<Plane*> all = {&hi.q, &hi.dq, &hi.ddq, &hi.dddq};
+  for (int k = 0; k < 11; k++)
+  {
+    po[k].h_out = outs[k];
+    po[k].planes = outs[k] ? rows[k] : 0;
+    po[k].ld = out->ld;
+    all.push_back(&po[k]);
+  }
+  HostPipe pipe;
+  RDB_TRY(pipe.init(in->n, 1 << 20, all));
+  int slot = 0;
+  for (int64_t off = 0; off < in->n; off += pipe.chunk, slot ^= 1)
+  {
+    const int64_t len = std::min<int64_t>(pipe.chunk, in->n - off);
+    RDB_TRY(pipe.h2d(hi.q, slot, off, len));
+    RDB_TRY(pipe.h2d(hi.dq, slot, off, len));
+    RDB_TRY(pipe.h2d(hi.ddq, slot, off, len));
+    RDB_TRY(pipe.h2d(hi.dddq, slot, off, len));
+    rdb_samples v = hi.view(slot, len, pipe.chunk);
+    rdb_kinematics_out o{pipe.chunk,    po[0].d[slot], po[1].d[slot], po[2].d[slot], po[3].d[slot],  po[4].d[slot],
+                         po[5].d[slot], po[6].d[slot], po[7].d[slot], po[8].d[slot], po[9].d[slot], po[10].d[slot]};
+    RDB_TRY(rdb_kinematics_batch(chain, &v, &o, pipe.st[slot]));
+    for (int k = 0; k < 11; k++) RDB_TRY(pipe.d2h(po[k], slot, off, len));
+  }
+  return pipe.finish();
+}
+
+static rdb_status dyn_host(const rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, double* inertia, int64_t ld_out, int what)
+{
+  RDB_TRY(check_samples(chain, in, true));
+  if (ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "ld_out < n");
+  const int n_in = chain->host.n_in;
+  HostIn hi;
+  hi.bind(in, n_in);
+  Plane pphi, ptau, pM;
+  pphi.h_out = phi; pphi.planes = phi ? (int64_t)10 * chain->host.nj * n_in : 0; pphi.ld = ld_out;
+  ptau.h_out = torque; ptau.planes = torque ? n_in : 0; ptau.ld = ld_out;
+  pM.h_out = inertia; pM.planes = inertia ? (int64_t)n_in * n_in : 0; pM.ld = ld_out;
+  HostPipe pipe;
+  RDB_TRY(pipe.init(in->n, phi ? (1 << 18) : (1 << 21), {&hi.q, &hi.dq, &hi.ddq, &hi.dddq, &pphi, &ptau, &pM}));
+  int slot = 0;
+  for (int64_t off = 0; off < in->n; off += pipe.chunk, slot ^= 1)
+  {
+    const int64_t len = std::min<int64_t>(pipe.chunk, in->n - off);
+    RDB_TRY(pipe.h2d(hi.q, slot, off, len));
+    RDB_TRY(pipe.h2d(hi.dq, slot, off, len));
+    RDB_TRY(pipe.h2d(hi.ddq, slot, off, len));
+    rdb_samples v = hi.view(slot, len, pipe.chunk);
+    if (what == 0) RDB_TRY(rdb_regressor_batch(chain, &v, pphi.d[slot], ptau.d[slot], pipe.chunk, pipe.st[slot]));
+    if (what == 1) RDB_TRY(rdb_torque_batch(chain, &v, ptau.d[slot], pipe.chunk, pipe.st[slot]));
+    if (what == 2) RDB_TRY(rdb_inertia_batch(chain, &v, pM.d[slot], pipe.chunk, pipe.st[slot]));
+    RDB_TRY(pipe.d2h(pphi, slot, off, len));
+    RDB_TRY(pipe.d2h(ptau, slot, off, len));
+    RDB_TRY(pipe.d2h(pM, slot, off, len));
+  }
+  return pipe.finish();
+}
+
+rdb_status rdb_torque_batch_host(const rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out)
+{
+  if (!torque) return fail(RDB_ERR_INVALID_ARG, "torque is null");
+  return dyn_host(chain, in, nullptr, torque, nullptr, ld_out, 1);
+}
+rdb_status rdb_regressor_batch_host(const rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, int64_t ld_out)
+{
+  if (!phi) return fail(RDB_ERR_INVALID_ARG, "phi is null");
+  if (in && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  return dyn_host(chain, in, phi, torque, nullptr, ld_out, 0);
+}
+rdb_status rdb_inertia_batch_host(const rdb_chain* chain, const rdb_samples* in, double* inertia, int64_t ld_out)
+{
+  if (!inertia) return fail(RDB_ERR_INVALID_ARG, "inertia is null");
+  return dyn_host(chain, in, nullptr, nullptr, inertia, ld_out, 2);
+}
+
+rdb_status rdb_regressor_gram_batch_host(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+                                         double* tau_sq, int32_t accumulate)
+{
+  RDB_TRY(check_samples(chain, in, true));
+  if (!in->dq || !in->ddq) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (!gram || !rhs) return fail(RDB_ERR_INVALID_ARG, "gram / rhs must not be null");
+  const int n_in = chain->host.n_in, P = 10 * chain->host.nj;
+  HostIn hi;
+  hi.bind(in, n_in);
+  Plane pt;
+  pt.h_in = tau_meas; pt.planes = tau_meas ? n_in : 0; pt.ld = in->ld;
+  HostPipe pipe;
+  RDB_TRY(pipe.init(in->n, 1 << 21, {&hi.q, &hi.dq, &hi.ddq, &hi.dddq, &pt}));
+  double* d_out = nullptr;  // gram | rhs | tau_sq
+  const size_t n_out = (size_t)P * P + P + 1;
+  RDB_CUDA(cudaMalloc(&d_out, n_out * sizeof(double)));
+  rdb_status s = RDB_OK;
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaStream_t acc = pipe.st[0];  // the accumulation is ordered on one stream; the other slot only stages copies
+  do
+  {
+    if (accumulate)
+    {
+      if (cudaMemcpyAsync(d_out, gram, sizeof(double) * P * P, cudaMemcpyHostToDevice, acc) != cudaSuccess ||
+          cudaMemcpyAsync(d_out + (size_t)P * P, rhs, sizeof(double) * P, cudaMemcpyHostToDevice, acc) != cudaSuccess ||
+          (tau_sq && cudaMemcpyAsync(d_out + (size_t)P * P + P, tau_sq, sizeof(double), cudaMemcpyHostToDevice, acc) != cudaSuccess))
+      {
+        s = cuda_fail(cudaGetLastError(), "gram_host upload");
+        break;
+      }
+      if (!tau_sq) cudaMemsetAsync(d_out + (size_t)P * P + P, 0, sizeof(double), acc);
+    }
+    for (int k = 0; k < 2; k++) cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
+    int slot = 0;
+    bool first = true;
+    for (int64_t off = 0; off < in->n && s == RDB_OK; off += pipe.chunk, slot ^= 1)
+    {
+      const int64_t len = std::min<int64_t>(pipe.chunk, in->n - off);
+      cudaStream_t cp = pipe.st[slot] ? pipe.st[slot] : pipe.st[0];
+      // staging buffer `slot` is free once the kernel that read it (two chunks ago) has finished
+      if (cp != acc) cudaStreamWaitEvent(cp, done[slot], 0);
+      const int sl = pipe.st[slot] ? slot : 0;
+      if ((s = pipe.h2d(hi.q, sl, off, len)) != RDB_OK) break;
+      if ((s = pipe.h2d(hi.dq, sl, off, len)) != RDB_OK) break;
+      if ((s = pipe.h2d(hi.ddq, sl, off, len)) != RDB_OK) break;
+      if ((s = pipe.h2d(pt, sl, off, len)) != RDB_OK) break;
+      cudaEvent_t copied;
+      cudaEventCreateWithFlags(&copied, cudaEventDisableTiming);
+      cudaEventRecord(copied, cp);
+      cudaStreamWaitEvent(acc, copied, 0);
+      cudaEventDestroy(copied);
+      rdb_samples v = hi.view(sl, len, pipe.chunk);
+      s = rdb_regressor_gram_batch(chain, &v, pt.d[sl], d_out, d_out + (size_t)P * P, d_out + (size_t)P * P + P, (accumulate || !first) ? 1 : 0, acc);
+      cudaEventRecord(done[slot], acc);
+      first = false;
+    }
+    if (s != RDB_OK) break;
+    if (in->n == 0 && !accumulate) cudaMemsetAsync(d_out, 0, n_out * sizeof(double), acc);
+    if (cudaMemcpyAsync(gram, d_out, sizeof(double) * P * P, cudaMemcpyDeviceToHost, acc) != cudaSuccess ||
+        cudaMemcpyAsync(rhs, d_out + (size_t)P * P, sizeof(double) * P, cudaMemcpyDeviceToHost, acc) != cudaSuccess ||
+        (tau_sq && cudaMemcpyAsync(tau_sq, d_out + (size_t)P * P + P, sizeof(double), cudaMemcpyDeviceToHost, acc) != cudaSuccess))
+    {
+      s = cuda_fail(cudaGetLastError(), "gram_host download");
+      break;
+    }
+    s = pipe.finish();
+  } while (0);
+  for (int k = 0; k < 2; k++)
+    if (done[k]) cudaEventDestroy(done[k]);
+  cudaDeviceSynchronize();
+  cudaFree(d_out);
+  return s;
+}
+
+}  // extern "C"

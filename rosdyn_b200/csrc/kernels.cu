@@ -1,0 +1,633 @@
+// kernels.cu -- hand-written sm_100a fp64 kernels for the rosdyn::Chain hot path.
+//
+// One thread walks the serial chain of one sample.  q/Dq/DDq/DDDq are read from SoA planes (one coalesced
+// 8-byte load per lane per plane, streamed), every result is written to SoA planes (coalesced streaming
+// stores), the model lives in the kernel-parameter constant bank (chain_dev.h).  Two families:
+//
+//   * kin_kernel      -- base-frame walker: everything the reference returns in the base frame
+//                        (frames, Jacobian, twist / acceleration / jerk recursions, RNEA torque);
+//                        replaces computeFrames/computeScrews/getJacobian/getTwist/getDTwist*/getDDTwist*/
+//                        getWrench/getJointTorque  (primitives_impl.h:863-1293).
+//   * dyn_kernel      -- link-frame walker for the dynamics that only need scalars per joint:
+//                        inertial regressor (getRegressor, primitives_impl.h:1295-1355), RNEA torque and the
+//                        joint inertia matrix (getJointInertia, primitives_impl.h:1357-1379).
+//
+// Both are FORWARD-ONLY: instead of the reference's backward wrench pass they carry, for every joint j
+// already passed, its unit twist ("Jacobian column") expressed at the current link, and project each
+// link's wrench / wrench-regressor on it.  That keeps the live state small enough for registers
+// (no per-link frame storage) and lets every output leave the thread the moment it is computed.
+#include <cuda_runtime.h>
+
+#include "launch.h"
+#include "spatial.cuh"
+
+namespace rdb
+{
+
+#define RDB_BLOCK 128
+
+template <int NJ_T>
+struct Cap
+{
+  static constexpr int value = NJ_T > 0 ? NJ_T : RDB_MAX_JOINTS;
+};
+
+// =============================================================================================================
+// link-frame walker
+// =============================================================================================================
+enum : int
+{
+  DYN_REGRESSOR = 1,  // write Phi
+  DYN_TORQUE = 2,     // write tau
+  DYN_INERTIA = 4     // write M
+};
+
+// Link-frame state of the walker after joint l: twist (v,w), acceleration (a,al) and gravity g of link l in link-l
+// axes at the link-l origin, and the unit twists (U[j],S[j]) of all joints j <= l at the same point/axes.
+template <int NJ_T, int MODE, class ChainT>
+__device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, double* __restrict__ phi, double* __restrict__ tau_out,
+                                         double* __restrict__ M_out, int64_t ld_out, int64_t i)
+{
+  constexpr int CAP = Cap<NJ_T>::value;
+  const int nj = NJ_T > 0 ? NJ_T : C.nj;
+  const int n_in = C.n_in;
+  constexpr bool kReg = (MODE & DYN_REGRESSOR) != 0;
+  constexpr bool kTau = (MODE & DYN_TORQUE) != 0;
+  constexpr bool kInr = (MODE & DYN_INERTIA) != 0;
+  constexpr bool kDyn = kReg || kTau;  // needs velocities / accelerations
+
+  V3 U[CAP], S[CAP];
+  double tau[kTau ? CAP : 1];
+  double M[kInr ? CAP * (CAP + 1) / 2 : 1];
+  if (kInr)
+  {
+#pragma unroll
+    for (int k = 0; k < (kInr ? CAP * (CAP + 1) / 2 : 1); k++)
+      if (NJ_T > 0 || k < nj * (nj + 1) / 2) M[k] = 0.0;
+  }
+
+  V3 v = v3(0, 0, 0), w = v3(0, 0, 0), a = v3(0, 0, 0), al = v3(0, 0, 0);
+  V3 g = v3(C.g);
+
+#pragma unroll
+  for (int l = 0; l < (NJ_T > 0 ? NJ_T : nj); l++)
+  {
+    const JointDev& J = C.joint[l];
+    const double ql = ld_in(in.q, J.in, in.ld, i);
+    double R[9];
+    V3 t;
+    joint_transform(J, ql, R, t);
+
+    // child-frame screw of joint l: [0;ax] revolute, [ax;0] prismatic, 0 fixed (R_pc^T axis_p == axis_j)
+    const V3 axj = v3(J.ax);
+    const V3 su = (J.type == RDB_JOINT_PRISMATIC) ? axj : v3(0, 0, 0);
+    const V3 ss = (J.type == RDB_JOINT_REVOLUTE) ? axj : v3(0, 0, 0);
+
+    if (kDyn)
+    {
+      const double dql = ld_in(in.dq, J.in, in.ld, i);
+      const double ddql = ld_in(in.ddq, J.in, in.ld, i);
+      // getTwist (primitives_impl.h:1007-1008) and getDTwist (1116-1117) moved to the child frame
+      v = rotT(R, cross_add(v, w, t));
+      w = rotT(R, w);
+      a = rotT(R, cross_add(a, al, t));
+      al = rotT(R, al);
+      g = rotT(R, g);
+      v = axpy(v, su, dql);
+      w = axpy(w, ss, dql);
+      // (v x s) Dq + s DDq, spatial cross of spacevect_algebra.h:88-93
+      const V3 xl = cross_add(cross(w, su), v, ss);
+      const V3 xa = cross(w, ss);
+      a = axpy(axpy(a, xl, dql), su, ddql);
+      al = axpy(axpy(al, xa, dql), ss, ddql);
+    }
+
+    // unit twists of the joints already passed, moved to link l
+#pragma unroll
+    for (int j = 0; j < l; j++)
+    {
+      U[j] = rotT(R, cross_add(U[j], S[j], t));
+      S[j] = rotT(R, S[j]);
+    }
+    U[l] = su;
+    S[l] = ss;
+    if (kTau) tau[l] = 0.0;
+
+    const double* P = C.link[l].pi;
+
+    if (kReg)
+    {
+      // Closed form of the wrench regressor of link l in link axes (primitives_impl.h:1324-1339):
+      //   col m    : [ fm ; 0 ]                         fm = a + w x v - g
+      //   col mc_k : [ (al^ + w^ w^) e_k ; e_k x fm ]
+      //   col I_p  : [ 0 ; E_p al + w x (E_p w) ]
+      // projected on the unit twist (u,s) of joint j (primitives_impl.h:1341-1347):
+      //   m   : u.fm
+      //   mc  : u x al + w x (w x u) + fm x s          (vector of the three mc columns)
+      //   I_p : s.(E_p al) + (s x w).(E_p w)
+      const V3 fm = cross_add(a - g, w, v);
+      const int64_t colbase = (int64_t)10 * l * n_in;
+#pragma unroll
+      for (int j = 0; j <= l; j++)
+      {
+        const int r = C.joint[j].in;
+        const V3 u = U[j], s = S[j];
+        const double e0 = dot(u, fm);
+        const V3 wu = cross(w, u);
+        const V3 h = cross_add(cross_add(cross(u, al), w, wu), fm, s);
+        const V3 rho = cross(s, w);
+        const double e4 = fma(s.x, al.x, rho.x * w.x);
+        const double e5 = fma(s.x, al.y, fma(s.y, al.x, fma(rho.x, w.y, rho.y * w.x)));
+        const double e6 = fma(s.x, al.z, fma(s.z, al.x, fma(rho.x, w.z, rho.z * w.x)));
+        const double e7 = fma(s.y, al.y, rho.y * w.y);
+        const double e8 = fma(s.y, al.z, fma(s.z, al.y, fma(rho.y, w.z, rho.z * w.y)));
+        const double e9 = fma(s.z, al.z, rho.z * w.z);
+        if (kTau)
+        {
+          double tj = tau[j];
+          tj = fma(e0, P[0], tj);
+          tj = fma(h.x, P[1], tj);
+          tj = fma(h.y, P[2], tj);
+          tj = fma(h.z, P[3], tj);
+          tj = fma(e4, P[4], tj);
+          tj = fma(e5, P[5], tj);
+          tj = fma(e6, P[6], tj);
+          tj = fma(e7, P[7], tj);
+          tj = fma(e8, P[8], tj);
+          tj = fma(e9, P[9], tj);
+          tau[j] = tj;
+        }
+        if (r >= 0)
+        {
+          double* o = phi + (colbase + r) * ld_out + i;
+          const int64_t st = (int64_t)n_in * ld_out;
+          __stcs(o, e0);
+          __stcs(o + st, h.x);
+          __stcs(o + 2 * st, h.y);
+          __stcs(o + 3 * st, h.z);
+          __stcs(o + 4 * st, e4);
+          __stcs(o + 5 * st, e5);
+          __stcs(o + 6 * st, e6);
+          __stcs(o + 7 * st, e7);
+          __stcs(o + 8 * st, e8);
+          __stcs(o + 9 * st, e9);
+        }
+      }
+      // rows of the joints after link l are structural zeros of this column block (exact 0.0)
+#pragma unroll
+      for (int j = l + 1; j < (NJ_T > 0 ? NJ_T : nj); j++)
+      {
+        const int r = C.joint[j].in;
+        if (r >= 0)
+        {
+          double* o = phi + (colbase + r) * ld_out + i;
+          const int64_t st = (int64_t)n_in * ld_out;
+#pragma unroll
+          for (int p = 0; p < 10; p++) __stcs(o + p * st, 0.0);
+        }
+      }
+    }
+    else if (kTau)
+    {
+      // RNEA wrench of link l about its origin in link axes (primitives_impl.h:1240-1250; gravity folded into a):
+      //   h(x,y) = I_cc [x;y] = [ m x + y x mc ; mc x x + I0 y ]
+      //   f = h_lin(a-g, al) + w x h_lin(v,w) ;  n = h_ang(a-g, al) + w x h_ang(v,w) + v x h_lin(v,w)
+      const V3 mc = v3(P[1], P[2], P[3]);
+      const V3 ag = a - g;
+      const V3 hl1 = cross_add(ag * P[0], al, mc);
+      const V3 hl2 = cross_add(v * P[0], w, mc);
+      const V3 Ial = v3(fma(P[4], al.x, fma(P[5], al.y, P[6] * al.z)), fma(P[5], al.x, fma(P[7], al.y, P[8] * al.z)),
+                        fma(P[6], al.x, fma(P[8], al.y, P[9] * al.z)));
+      const V3 Iw = v3(fma(P[4], w.x, fma(P[5], w.y, P[6] * w.z)), fma(P[5], w.x, fma(P[7], w.y, P[8] * w.z)),
+                       fma(P[6], w.x, fma(P[8], w.y, P[9] * w.z)));
+      const V3 ha1 = cross_add(Ial, mc, ag);
+      const V3 ha2 = cross_add(Iw, mc, v);
+      const V3 f = cross_add(hl1, w, hl2);
+      const V3 n = cross_add(cross_add(ha1, w, ha2), v, hl2);
+#pragma unroll
+      for (int j = 0; j <= l; j++) tau[j] += dot(U[j], f) + dot(S[j], n);
+    }
+
+    if (kInr)
+    {
+      // M += J_l^T I_cc(l) J_l with J_l = unit twists at link l in link axes (primitives_impl.h:1366-1375)
+      const V3 mc = v3(P[1], P[2], P[3]);
+#pragma unroll
+      for (int j = 0; j <= l; j++)
+      {
+        const V3 u = U[j], s = S[j];
+        const V3 hl = cross_add(u * P[0], s, mc);
+        const V3 Is = v3(fma(P[4], s.x, fma(P[5], s.y, P[6] * s.z)), fma(P[5], s.x, fma(P[7], s.y, P[8] * s.z)),
+                         fma(P[6], s.x, fma(P[8], s.y, P[9] * s.z)));
+        const V3 ha = cross_add(Is, mc, u);
+#pragma unroll
+        for (int k = 0; k <= j; k++) M[j * (j + 1) / 2 + k] += dot(U[k], hl) + dot(S[k], ha);
+      }
+    }
+  }
+
+  if (kTau)
+  {
+#pragma unroll
+    for (int j = 0; j < (NJ_T > 0 ? NJ_T : nj); j++)
+    {
+      const int r = C.joint[j].in;
+      if (r >= 0) st_out(tau_out, r, ld_out, i, tau[j]);
+    }
+  }
+  if (kInr)
+  {
+#pragma unroll
+    for (int j = 0; j < (NJ_T > 0 ? NJ_T : nj); j++)
+#pragma unroll
+      for (int k = 0; k <= j; k++)
+      {
+        const int rj = C.joint[j].in, rk = C.joint[k].in;
+        if (rj >= 0 && rk >= 0)
+        {
+          const double m = M[j * (j + 1) / 2 + k];
+          st_out(M_out, (int64_t)rj * n_in + rk, ld_out, i, m);
+          if (j != k) st_out(M_out, (int64_t)rk * n_in + rj, ld_out, i, m);
+        }
+      }
+  }
+}
+
+template <int NJ, int MODE>
+__global__ void __launch_bounds__(RDB_BLOCK) dyn_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, double* __restrict__ phi,
+                                                        double* __restrict__ tau, double* __restrict__ M, int64_t ld_out)
+{
+  const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
+  if (i >= in.n) return;
+  dyn_body<NJ, MODE>(C, in, phi, tau, M, ld_out, i);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RDB_BLOCK) dyn_kernel_generic(const ChainDev<RDB_MAX_JOINTS>* __restrict__ C, const SamplesDev in,
+                                                                double* __restrict__ phi, double* __restrict__ tau, double* __restrict__ M,
+                                                                int64_t ld_out)
+{
+  const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
+  if (i >= in.n) return;
+  dyn_body<0, MODE>(*C, in, phi, tau, M, ld_out, i);
+}
+
+// =============================================================================================================
+// base-frame walker
+// =============================================================================================================
+struct Tw
+{
+  V3 l, a;  // linear, angular
+};
+__device__ __forceinline__ Tw tw0() { return Tw{v3(0, 0, 0), v3(0, 0, 0)}; }
+// spatialTranslation, spacevect_algebra.h:129-133
+__device__ __forceinline__ Tw transl(Tw t, V3 d) { return Tw{cross_add(t.l, t.a, d), t.a}; }
+// spatialCrossProduct, spacevect_algebra.h:88-93
+__device__ __forceinline__ Tw scross(Tw a, Tw b) { return Tw{cross_add(cross(a.a, b.l), a.l, b.a), cross(a.a, b.a)}; }
+__device__ __forceinline__ Tw tw_axpy(Tw y, Tw x, double s) { return Tw{axpy(y.l, x.l, s), axpy(y.a, x.a, s)}; }
+__device__ __forceinline__ void st_tw(double* p, int link, int64_t ld, int64_t i, Tw t)
+{
+  st3(p, (int64_t)6 * link, ld, i, t.l);
+  st3(p, (int64_t)6 * link + 3, ld, i, t.a);
+}
+__device__ __forceinline__ void st_pose(double* p, int64_t plane0, int64_t ld, int64_t i, const double* R, V3 t)
+{
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+  {
+    __stcs(p + (plane0 + 4 * r + 0) * ld + i, R[3 * r + 0]);
+    __stcs(p + (plane0 + 4 * r + 1) * ld + i, R[3 * r + 1]);
+    __stcs(p + (plane0 + 4 * r + 2) * ld + i, R[3 * r + 2]);
+    __stcs(p + (plane0 + 4 * r + 3) * ld + i, r == 0 ? t.x : (r == 1 ? t.y : t.z));
+  }
+}
+
+template <int NJ_T, unsigned MASK, class ChainT>
+__device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, const KinOutDev& o, int64_t i)
+{
+  constexpr int CAP = Cap<NJ_T>::value;
+  const int nj = NJ_T > 0 ? NJ_T : C.nj;
+  const int n_in = C.n_in;
+  const int64_t ld = o.ld;
+
+  constexpr bool cJer = (MASK & (K_DDTWIST | K_DDTWIST_NONLIN)) != 0;
+  constexpr bool cAcc = (MASK & (K_DTWIST | K_TORQUE)) != 0 || cJer;
+  constexpr bool cVel = (MASK & (K_TWIST | K_DTWIST_NONLIN)) != 0 || cAcc;
+  constexpr bool cJac = (MASK & (K_JAC | K_TORQUE)) != 0;
+
+  const bool wTl = (MASK & K_TLINKS) && o.T_links;
+  const bool wV = (MASK & K_TWIST) && o.twist;
+  const bool wA = (MASK & K_DTWIST) && o.dtwist;
+  const bool wAl = (MASK & K_DTWIST_LIN) && o.dtwist_lin;
+  const bool wAn = (MASK & K_DTWIST_NONLIN) && o.dtwist_nonlin;
+  const bool wJ = (MASK & K_DDTWIST) && o.ddtwist;
+  const bool wJl = (MASK & K_DDTWIST_LIN) && o.ddtwist_lin;
+  const bool wJn = (MASK & K_DDTWIST_NONLIN) && o.ddtwist_nonlin;
+  const bool wTau = (MASK & K_TORQUE) && o.torque;
+
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // base <- current link
+  V3 p = v3(0, 0, 0);
+  Tw v = tw0(), a = tw0(), al = tw0(), an = tw0(), jf = tw0(), jl = tw0(), jn = tw0();
+  V3 sl[cJac ? CAP : 1], sa[cJac ? CAP : 1], pj[cJac ? CAP : 1];
+  double tau[(MASK & K_TORQUE) ? CAP : 1];
+
+  // link 0 = base: identity pose, zero twists (primitives_impl.h:661-677, 697)
+  if (wTl) st_pose(o.T_links, 0, ld, i, R, p);
+  if (wV) st_tw(o.twist, 0, ld, i, v);
+  if (wA) st_tw(o.dtwist, 0, ld, i, v);
+  if (wAl) st_tw(o.dtwist_lin, 0, ld, i, v);
+  if (wAn) st_tw(o.dtwist_nonlin, 0, ld, i, v);
+  if (wJ) st_tw(o.ddtwist, 0, ld, i, v);
+  if (wJl) st_tw(o.ddtwist_lin, 0, ld, i, v);
+  if (wJn) st_tw(o.ddtwist_nonlin, 0, ld, i, v);
+
+#pragma unroll
+  for (int l = 0; l < (NJ_T > 0 ? NJ_T : nj); l++)
+  {
+    const JointDev& J = C.joint[l];
+    const double ql = ld_in(in.q, J.in, in.ld, i);
+    double Rpc[9];
+    V3 t;
+    joint_transform(J, ql, Rpc, t);
+
+    // computeScrews (primitives_impl.h:879): screw of joint l in the base frame uses the PARENT link rotation
+    const V3 axb = rot(R, v3(J.axp));
+    Tw s;
+    s.l = (J.type == RDB_JOINT_PRISMATIC) ? axb : v3(0, 0, 0);
+    s.a = (J.type == RDB_JOINT_REVOLUTE) ? axb : v3(0, 0, 0);
+
+    // computeFrames (primitives_impl.h:869)
+    const V3 d = rot(R, t);  // p_l - p_{l-1}
+    p = p + d;
+    double Rn[9];
+    mul33(R, Rpc, Rn);
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = Rn[k];
+    if (wTl) st_pose(o.T_links, (int64_t)12 * (l + 1), ld, i, R, p);
+
+    if (cJac)
+    {
+      sl[l] = s.l;
+      sa[l] = s.a;
+      pj[l] = p;
+    }
+
+    const double dql = (cVel) ? ld_in(in.dq, J.in, in.ld, i) : 0.0;
+    const double ddql = (MASK & (K_DTWIST | K_DTWIST_LIN | K_TORQUE)) || cJer ? ld_in(in.ddq, J.in, in.ld, i) : 0.0;
+    const double dddql = (MASK & (K_DDTWIST | K_DDTWIST_LIN)) ? ld_in(in.dddq, J.in, in.ld, i) : 0.0;
+
+    Tw vxs = tw0();
+    if (cVel)
+    {
+      v = tw_axpy(transl(v, d), s, dql);  // primitives_impl.h:1007-1008
+      vxs = scross(v, s);
+      if (wV) st_tw(o.twist, l + 1, ld, i, v);
+    }
+    if (MASK & K_DTWIST_LIN)
+    {
+      al = tw_axpy(transl(al, d), s, ddql);  // primitives_impl.h:1055-1056
+      if (wAl) st_tw(o.dtwist_lin, l + 1, ld, i, al);
+    }
+    if (MASK & K_DTWIST_NONLIN)
+    {
+      an = tw_axpy(transl(an, d), vxs, dql);  // primitives_impl.h:1074-1075
+      if (wAn) st_tw(o.dtwist_nonlin, l + 1, ld, i, an);
+    }
+    if (cAcc)
+    {
+      a = tw_axpy(tw_axpy(transl(a, d), vxs, dql), s, ddql);  // primitives_impl.h:1116-1117
+      if (wA) st_tw(o.dtwist, l + 1, ld, i, a);
+    }
+    if (MASK & K_DDTWIST_LIN)
+    {
+      jl = tw_axpy(transl(jl, d), s, dddql);  // primitives_impl.h:1148-1149
+      if (wJl) st_tw(o.ddtwist_lin, l + 1, ld, i, jl);
+    }
+    if (cJer)
+    {
+      // primitives_impl.h:1213-1218 / 1174-1178; the reference's 1x coefficient on (v x s) DDq is mirrored
+      const Tw axs = scross(a, s);
+      const Tw vvxs = scross(v, vxs);
+      const Tw k = Tw{axs.l + vvxs.l, axs.a + vvxs.a};
+      if (MASK & K_DDTWIST)
+      {
+        jf = tw_axpy(tw_axpy(tw_axpy(transl(jf, d), s, dddql), vxs, ddql), k, dql);
+        if (wJ) st_tw(o.ddtwist, l + 1, ld, i, jf);
+      }
+      if (MASK & K_DDTWIST_NONLIN)
+      {
+        jn = tw_axpy(tw_axpy(transl(jn, d), vxs, ddql), k, dql);
+        if (wJn) st_tw(o.ddtwist_nonlin, l + 1, ld, i, jn);
+      }
+    }
+
+    if (MASK & K_TORQUE)
+    {
+      // getWrench (primitives_impl.h:1240-1250) for link l+1, then getJointTorque (1267-1271) as a forward
+      // projection: tau_j = s_j . sum_{m>=j} dualTransl(w_m, p_j - p_m)   (spacevect_algebra.h:150-154)
+      tau[l] = 0.0;
+      const double* P = C.link[l].pi;
+      const V3 mc = v3(P[1], P[2], P[3]);
+      const V3 agl = rotT(R, a.l - v3(C.g));
+      const V3 all = rotT(R, a.a);
+      const V3 vl = rotT(R, v.l);
+      const V3 wl = rotT(R, v.a);
+      const V3 hl1 = cross_add(agl * P[0], all, mc);
+      const V3 hl2 = cross_add(vl * P[0], wl, mc);
+      const V3 Ial = v3(fma(P[4], all.x, fma(P[5], all.y, P[6] * all.z)), fma(P[5], all.x, fma(P[7], all.y, P[8] * all.z)),
+                        fma(P[6], all.x, fma(P[8], all.y, P[9] * all.z)));
+      const V3 Iw = v3(fma(P[4], wl.x, fma(P[5], wl.y, P[6] * wl.z)), fma(P[5], wl.x, fma(P[7], wl.y, P[8] * wl.z)),
+                       fma(P[6], wl.x, fma(P[8], wl.y, P[9] * wl.z)));
+      const V3 ha1 = cross_add(Ial, mc, agl);
+      const V3 ha2 = cross_add(Iw, mc, vl);
+      const V3 f = rot(R, cross_add(hl1, wl, hl2));
+      const V3 n = rot(R, cross_add(cross_add(ha1, wl, ha2), vl, hl2));
+#pragma unroll
+      for (int j = 0; j <= l; j++)
+      {
+        const V3 dj = pj[j] - p;
+        tau[j] += dot(sl[j], f) + dot(sa[j], cross_add(n, f, dj));
+      }
+    }
+  }
+
+  if ((MASK & K_TTOOL) && o.T_tool) st_pose(o.T_tool, 0, ld, i, R, p);
+
+  if ((MASK & K_JAC) && o.jacobian)
+  {
+    // getJacobian (primitives_impl.h:939-945): col = spatialTranslation(s_j, p_tool - p_j)
+#pragma unroll
+    for (int j = 0; j < (NJ_T > 0 ? NJ_T : nj); j++)
+    {
+      const int r = C.joint[j].in;
+      if (r >= 0)
+      {
+        const V3 lin = cross_add(sl[j], sa[j], p - pj[j]);
+        st3(o.jacobian, (int64_t)6 * r, ld, i, lin);
+        st3(o.jacobian, (int64_t)6 * r + 3, ld, i, sa[j]);
+      }
+    }
+  }
+  if (wTau)
+  {
+#pragma unroll
+    for (int j = 0; j < (NJ_T > 0 ? NJ_T : nj); j++)
+    {
+      const int r = C.joint[j].in;
+      if (r >= 0) st_out(o.torque, r, ld, i, tau[j]);
+    }
+  }
+  (void)n_in;
+}
+
+template <int NJ, unsigned MASK>
+__global__ void __launch_bounds__(RDB_BLOCK) kin_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const KinOutDev o)
+{
+  const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
+  if (i >= in.n) return;
+  kin_body<NJ, MASK>(C, in, o, i);
+}
+
+template <unsigned MASK>
+__global__ void __launch_bounds__(RDB_BLOCK) kin_kernel_generic(const ChainDev<RDB_MAX_JOINTS>* __restrict__ C, const SamplesDev in,
+                                                                const KinOutDev o)
+{
+  const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
+  if (i >= in.n) return;
+  kin_body<0, MASK>(*C, in, o, i);
+}
+
+// =============================================================================================================
+// synthetic inputs
+// =============================================================================================================
+__host__ __device__ inline uint64_t splitmix64(uint64_t x)
+{
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ inline double uniform_pm1(uint64_t seed, int64_t i, int stream_id, int plane)
+{
+  const uint64_t z = splitmix64(seed + ((uint64_t)i << 8) + ((uint64_t)stream_id << 6) + (uint64_t)plane);
+  return 2.0 * ((double)(z >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+}
+__global__ void fill_uniform_kernel(double* x, int n_planes, int64_t n, int64_t ld, uint64_t seed, int stream_id)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int j = 0; j < n_planes; j++) x[(int64_t)j * ld + i] = uniform_pm1(seed, i, stream_id, j);
+}
+void fill_uniform_host(double* x, int n_planes, int64_t n, int64_t ld, uint64_t seed, int stream_id)
+{
+  for (int j = 0; j < n_planes; j++)
+    for (int64_t i = 0; i < n; i++) x[(int64_t)j * ld + i] = uniform_pm1(seed, i, stream_id, j);
+}
+
+// =============================================================================================================
+// launchers
+// =============================================================================================================
+template <int NJ>
+static ChainDev<NJ> narrow(const ChainDev<RDB_MAX_JOINTS>& h)
+{
+  ChainDev<NJ> c;
+  c.nj = h.nj;
+  c.n_in = h.n_in;
+  for (int k = 0; k < 3; k++) c.g[k] = h.g[k];
+  for (int j = 0; j < NJ; j++)
+  {
+    c.joint[j] = h.joint[j];
+    c.link[j] = h.link[j];
+  }
+  return c;
+}
+
+static inline unsigned grid_for(int64_t n) { return (unsigned)((n + RDB_BLOCK - 1) / RDB_BLOCK); }
+
+#define RDB_FAST_NJ(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+
+template <int MODE>
+static cudaError_t launch_dyn_mode(const ChainHost& ch, const SamplesDev& in, double* phi, double* tau, double* M, int64_t ld_out,
+                                   cudaStream_t st)
+{
+  if (in.n <= 0) return cudaSuccess;
+  const unsigned grid = grid_for(in.n);
+  switch (ch.host.nj)
+  {
+#define X(N)                                                                                   \
+  case N:                                                                                      \
+    dyn_kernel<N, MODE><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(ch.host), in, phi, tau, M, ld_out); \
+    break;
+    RDB_FAST_NJ(X)
+#undef X
+    default:
+      dyn_kernel_generic<MODE><<<grid, RDB_BLOCK, 0, st>>>(ch.dev, in, phi, tau, M, ld_out);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dyn(const ChainHost& ch, int mode, const SamplesDev& in, double* phi, double* tau, double* M, int64_t ld_out,
+                       cudaStream_t st)
+{
+  switch (mode)
+  {
+    case DYN_REGRESSOR: return launch_dyn_mode<DYN_REGRESSOR>(ch, in, phi, tau, M, ld_out, st);
+    case DYN_REGRESSOR | DYN_TORQUE: return launch_dyn_mode<DYN_REGRESSOR | DYN_TORQUE>(ch, in, phi, tau, M, ld_out, st);
+    case DYN_TORQUE: return launch_dyn_mode<DYN_TORQUE>(ch, in, phi, tau, M, ld_out, st);
+    case DYN_INERTIA: return launch_dyn_mode<DYN_INERTIA>(ch, in, phi, tau, M, ld_out, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <unsigned MASK>
+static cudaError_t launch_kin_mask(const ChainHost& ch, const SamplesDev& in, const KinOutDev& o, cudaStream_t st)
+{
+  if (in.n <= 0) return cudaSuccess;
+  const unsigned grid = grid_for(in.n);
+  switch (ch.host.nj)
+  {
+#define X(N)                                                                   \
+  case N:                                                                      \
+    kin_kernel<N, MASK><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(ch.host), in, o); \
+    break;
+    RDB_FAST_NJ(X)
+#undef X
+    default:
+      kin_kernel_generic<MASK><<<grid, RDB_BLOCK, 0, st>>>(ch.dev, in, o);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+// compiled output combinations, smallest first; the launcher takes the first that covers the request
+static constexpr unsigned KM_POSE = K_TTOOL | K_TLINKS;
+static constexpr unsigned KM_POSE_JAC = K_TTOOL | K_TLINKS | K_JAC;
+static constexpr unsigned KM_VEL = KM_POSE_JAC | K_TWIST;
+static constexpr unsigned KM_ACC = KM_VEL | K_DTWIST | K_DTWIST_LIN | K_DTWIST_NONLIN;
+static constexpr unsigned KM_CFG2 = K_TTOOL | K_JAC | K_TWIST | K_DTWIST | K_TORQUE;  // BASELINE.json configs[1]
+static constexpr unsigned KM_JERK = K_TWIST | K_DTWIST | K_DDTWIST;                   // BASELINE.json configs[4]
+
+cudaError_t launch_kin(const ChainHost& ch, unsigned want, const SamplesDev& in, const KinOutDev& o, cudaStream_t st)
+{
+#define TRY(M) \
+  if ((want & ~(M)) == 0) return launch_kin_mask<M>(ch, in, o, st);
+  TRY(KM_POSE)
+  TRY(KM_POSE_JAC)
+  TRY(KM_VEL)
+  TRY(KM_CFG2)
+  TRY(KM_JERK)
+  TRY(KM_ACC)
+#undef TRY
+  return launch_kin_mask<K_ALL>(ch, in, o, st);
+}
+
+cudaError_t launch_fill_uniform(double* x, int n_planes, int64_t n, int64_t ld, uint64_t seed, int stream_id, cudaStream_t st)
+{
+  if (n <= 0) return cudaSuccess;
+  fill_uniform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n_planes, n, ld, seed, stream_id);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace rdb

@@ -1,0 +1,51 @@
+// launch.h -- host-side handle contents and kernel launcher declarations (internal).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "chain_dev.h"
+
+namespace rdb
+{
+
+struct GramWorkspace
+{
+  double* partials = nullptr;  // per-CTA partial normal equations
+  size_t bytes = 0;
+  int ctas = 0;
+};
+
+struct ChainHost
+{
+  ChainDev<RDB_MAX_JOINTS> host;           // model constants, host copy
+  ChainDev<RDB_MAX_JOINTS>* dev = nullptr;  // same, in device memory (generic kernels)
+  int device = 0;
+  bool inputs_cover_all = true;  // every input index is fed by a chain joint (else outputs are pre-zeroed)
+  double nominal[10 * RDB_MAX_JOINTS];
+  GramWorkspace gram;
+  int sm_count = 148;
+};
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+cudaError_t launch_dyn(const ChainHost& ch, int mode, const SamplesDev& in, double* phi, double* tau, double* M, int64_t ld_out,
+                       cudaStream_t st);
+cudaError_t launch_kin(const ChainHost& ch, unsigned want, const SamplesDev& in, const KinOutDev& o, cudaStream_t st);
+cudaError_t launch_fill_uniform(double* x, int n_planes, int64_t n, int64_t ld, uint64_t seed, int stream_id, cudaStream_t st);
+void fill_uniform_host(double* x, int n_planes, int64_t n, int64_t ld, uint64_t seed, int stream_id);
+
+// gram.cu
+cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
+                        int accumulate, cudaStream_t st);
+cudaError_t fp64_peak(int kind, int reps, double* tflops);
+
+enum : int
+{
+  DYN_REGRESSOR_ = 1,
+  DYN_TORQUE_ = 2,
+  DYN_INERTIA_ = 4
+};
+
+}  // namespace rdb
