@@ -80,7 +80,10 @@ def test_against_oracle_seeded(name, chains, torch):
     P = 10 * d.n_joints
     planes = _np(phi.transpose(0, 1).reshape(P * d.n_inputs, n))
     assert_close(planes, rphi, f"{name}:regressor")
-    assert np.array_equal(planes == 0.0, rphi == 0.0) or np.all(planes[rphi == 0.0] == 0.0), "structural zeros must be exact"
+    Phi = planes.reshape(P, d.n_inputs, n)
+    for j, jd in enumerate(d.joints):  # block upper-triangular: exact zeros in the column blocks of the links before joint j
+        if jd.input_index >= 0:
+            assert np.all(Phi[:10 * j, jd.input_index, :] == 0.0), "structural zeros must be exact"
     assert_close(_np(tau), rtau, f"{name}:torque via regressor pass")
     assert_close(_np(ch.getRegressor(q, dq, ddq)).reshape(-1), _np(phi).reshape(-1), "regressor without torque", 0.0)
     assert_close(_np(ch.getJointTorque(q, dq, ddq)), rtau, f"{name}:torque")
