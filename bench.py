@@ -300,13 +300,14 @@ def main():
     if gram:
         # algorithmic FLOPs per sample, BLAS SYRK+GEMV convention: n_act*P*(P+1) + 2*n_act*P
         flop = n_in * P * (P + 1) + 2 * n_in * P
-        peak = None
+        peak, peaks64 = None, None
         if rank == 0:
-            peak = max(fp64_peak("dmma", 3), fp64_peak("dfma", 3))
+            peaks64 = {"dmma_m8n8k4": fp64_peak("dmma", 3), "dfma": fp64_peak("dfma", 3)}
+            peak = max(peaks64.values())
         ach = S * flop / (ms * 1e-3 / args.steps) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None, "traffic": None,
                 "peak_source": "own FP64 micro-benchmark on this GPU (max of DMMA m8n8k4 and DFMA); MEASURED_PEAKS.json has no FP64 figure",
-                "flop_per_sample": flop, "kernel": "regressor+gram step (all kernels of the step)"}
+                "fp64_peaks_tflops": peaks64, "flop_per_sample": flop, "kernel": "gram_fused_kernel<7> (regressor generation + DMMA normal equations)"}
     else:
         bytes_per_sample = 8 * (3 * n_in + P * n_in + n_in)          # 3552 B for C6
         ach = S * bytes_per_sample / (ms * 1e-3 / args.steps) / 1e9

@@ -130,7 +130,7 @@ static rdb_status check_samples(const ChainHost* ch, const rdb_samples* in, bool
 {
   if (!ch || !in) return fail(RDB_ERR_INVALID_ARG, "null chain or samples");
   if (in->n < 0 || in->ld < in->n) return fail(RDB_ERR_INVALID_ARG, "samples: need 0 <= n <= ld");
-  if (need_q && !in->q && ch->host.n_in > 0) return fail(RDB_ERR_DIM_MISMATCH, "q is required");
+  if (need_q && !in->q && ch->host.n_in > 0 && in->n > 0) return fail(RDB_ERR_DIM_MISMATCH, "q is required");
   return RDB_OK;
 }
 
@@ -230,6 +230,7 @@ void rdb_chain_destroy(rdb_chain* chain)
   if (!chain) return;
   if (chain->dev) cudaFree(chain->dev);
   if (chain->gram.partials) cudaFree(chain->gram.partials);
+  if (chain->gram.fused_partials) cudaFree(chain->gram.fused_partials);
   delete chain;
 }
 
@@ -295,6 +296,7 @@ rdb_status rdb_torque_batch(const rdb_chain* chain, const rdb_samples* in, doubl
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  if (in->n == 0) return RDB_OK;
   if (!torque || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "torque: null or ld_out < n");
   cudaStream_t st = (cudaStream_t)stream;
   if ((s = prezero(chain, torque, chain->host.n_in, ld_out, in->n, st)) != RDB_OK) return s;
@@ -307,7 +309,8 @@ rdb_status rdb_regressor_batch(const rdb_chain* chain, const rdb_samples* in, do
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
   // Chain::getRegressor throws std::invalid_argument("Input data dimensions mismatch") (primitives_impl.h:1299-1309)
-  if (!in->dq || !in->ddq) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (in->n == 0) return RDB_OK;
   if (!phi || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "phi: null or ld_out < n");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_in = chain->host.n_in;
@@ -321,6 +324,7 @@ rdb_status rdb_inertia_batch(const rdb_chain* chain, const rdb_samples* in, doub
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  if (in->n == 0) return RDB_OK;
   if (!inertia || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "inertia: null or ld_out < n");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_in = chain->host.n_in;
@@ -334,7 +338,7 @@ rdb_status rdb_regressor_gram_batch(const rdb_chain* chain, const rdb_samples* i
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
-  if (!in->dq || !in->ddq) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
   if (!gram || !rhs) return fail(RDB_ERR_INVALID_ARG, "gram / rhs must not be null");
   RDB_CUDA(launch_gram(*const_cast<rdb_chain*>(chain), to_dev(in), tau_meas, gram, rhs, tau_sq, accumulate, (cudaStream_t)stream));
   return RDB_OK;

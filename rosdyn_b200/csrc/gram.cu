@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "launch.h"
 
@@ -170,6 +171,15 @@ cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_m
       if (tau_sq) cudaMemsetAsync(tau_sq, 0, sizeof(double), st);
     }
     return cudaGetLastError();
+  }
+  {
+    // fused warp-specialised kernel (gram_fused.cu) whenever the chain fits it; RDB_GRAM_IMPL=v0 forces the general pipeline
+    static const bool force_v0 = [] { const char* e = getenv("RDB_GRAM_IMPL"); return e && e[0] == 'v'; }();
+    if (!force_v0)
+    {
+      cudaError_t e = launch_gram_fused(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
+      if (e != cudaErrorNotSupported) return e;
+    }
   }
   const int nblk = (P + 1 + BLK - 1) / BLK;
   const int npairs = nblk * (nblk + 1) / 2;

@@ -14,6 +14,8 @@ struct GramWorkspace
   double* partials = nullptr;  // per-CTA partial normal equations
   size_t bytes = 0;
   int ctas = 0;
+  double* fused_partials = nullptr;  // gram_fused.cu: per-CTA partial (P+1)x(P+1) upper-triangular tiles
+  size_t fused_bytes = 0;
 };
 
 struct ChainHost
@@ -40,6 +42,9 @@ void fill_uniform_host(double* x, int n_planes, int64_t n, int64_t ld, uint64_t 
 cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
                         int accumulate, cudaStream_t st);
 cudaError_t fp64_peak(int kind, int reps, double* tflops);
+// gram_fused.cu: cudaErrorNotSupported when the chain does not fit the fused kernel
+cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
+                              int accumulate, cudaStream_t st);
 
 enum : int
 {
