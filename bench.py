@@ -182,6 +182,7 @@ def main():
     import torch.distributed as dist
     from rosdyn_b200 import fixtures
     from rosdyn_b200.chain import Chain, fill_uniform, fp64_peak, kernel_launch_count
+    from rosdyn_b200.sharding import allreduce_normal_equations
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,10 +218,7 @@ def main():
         if gram:
             check(lib.rdb_regressor_gram_batch(ch._h, ctypes.byref(smp), None, G.data_ptr(), b.data_ptr(), tt.data_ptr(), 0, st))
             if world > 1:   # the one exchange step of the path: sum the small normal-equation partials over NVLink
-                flat[:P * P].copy_(G.reshape(-1))
-                flat[P * P:P * P + P].copy_(b)
-                flat[P * P + P:].copy_(tt)
-                dist.all_reduce(flat)
+                allreduce_normal_equations(G, b, tt, flat=flat)
         else:
             check(lib.rdb_regressor_batch(ch._h, ctypes.byref(smp), phi.data_ptr(), tau.data_ptr(), S, st))
 
@@ -302,8 +300,8 @@ def main():
         flop = n_in * P * (P + 1) + 2 * n_in * P
         peak, peaks64 = None, None
         if rank == 0:
-            peaks64 = {"dmma_m8n8k4": fp64_peak("dmma", 3), "dfma": fp64_peak("dfma", 3)}
-            peak = max(peaks64.values())
+            peaks64 = {"dmma_m8n8k4": fp64_peak("dmma", 3), "dfma": fp64_peak("dfma", 3), "dmma_and_dfma_interleaved": fp64_peak("mixed", 3)}
+            peak = max(peaks64["dmma_m8n8k4"], peaks64["dfma"])
         ach = S * flop / (ms * 1e-3 / args.steps) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None, "traffic": None,
                 "peak_source": "own FP64 micro-benchmark on this GPU (max of DMMA m8n8k4 and DFMA); MEASURED_PEAKS.json has no FP64 figure",

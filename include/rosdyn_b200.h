@@ -170,7 +170,7 @@ rdb_status rdb_fill_uniform(double* x, int32_t n_planes, int64_t n, int64_t ld, 
 void rdb_fill_uniform_host(double* x, int32_t n_planes, int64_t n, int64_t ld, uint64_t seed, int32_t stream_id);
 
 /* FP64 pipe micro-benchmarks (own roofline denominator; MEASURED_PEAKS.json carries no FP64 figure).
- * kind 0 = DFMA, 1 = DMMA m8n8k4.  Returns achieved TFLOP/s in *tflops (CUDA-event timed, best of reps). */
+ * kind 0 = DFMA, 1 = DMMA m8n8k4, 2 = both interleaved (flops summed).  Returns achieved TFLOP/s in *tflops (CUDA-event timed, best of reps). */
 rdb_status rdb_fp64_peak(int32_t kind, int32_t reps, double* tflops);
 
 #ifdef __cplusplus

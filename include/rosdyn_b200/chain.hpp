@@ -1,0 +1,257 @@
+// chain.hpp -- C++ facade over the C-ABI (rosdyn_b200.h) with the method names of rosdyn::Chain
+// (reference: rosdyn_core/include/rosdyn_core/primitives.h:235-555).
+//
+// * per-sample getters take/return std containers laid out exactly like the reference's Eigen objects
+//   (column-major matrices, 6-vectors linear-then-angular) and run as N = 1 batches on the GPU;
+// * batched siblings take SoA arrays (host or device) and forward to the C-ABI;
+// * optional Eigen-typed overloads appear when <Eigen/Core> is available (it is not in the build image,
+//   so they are compile-tested only where Eigen exists).
+// Errors follow the reference: std::runtime_error from the constructor (primitives_impl.h:498-501),
+// std::invalid_argument("Input data dimensions mismatch") from getRegressor (primitives_impl.h:1299-1309).
+// Like the reference class, one object serves one thread at a time.
+#ifndef ROSDYN_B200_CHAIN_HPP
+#define ROSDYN_B200_CHAIN_HPP
+
+#include <array>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../rosdyn_b200.h"
+
+#if defined(__has_include)
+#if __has_include(<Eigen/Core>)
+#include <Eigen/Core>
+#define ROSDYN_B200_HAVE_EIGEN 1
+#endif
+#endif
+
+namespace rosdyn_b200
+{
+
+using Vector6d = std::array<double, 6>;
+using VectorXd = std::vector<double>;
+using Affine3dImage = std::array<double, 16>;  // 4x4 column-major, the memory image of Eigen::Affine3d
+
+// URDF rpy -> row-major rotation, R = Rz(yaw) Ry(pitch) Rx(roll) (urdf_parser.h:44-50 via the URDF quaternion)
+inline void rpyToRot(double r, double p, double y, double R[9])
+{
+  const double cr = std::cos(r), sr = std::sin(r), cp = std::cos(p), sp = std::sin(p), cy = std::cos(y), sy = std::sin(y);
+  R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
+  R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
+  R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+}
+
+class Chain
+{
+public:
+  explicit Chain(const rdb_chain_desc& desc)
+  {
+    const rdb_status s = rdb_chain_create(&desc, &m_h);
+    if (s != RDB_OK) throw std::runtime_error(std::string("rosdyn_b200: ") + rdb_last_error());
+    m_nj = rdb_chain_joints_number(m_h);
+    m_nl = rdb_chain_links_number(m_h);
+    m_n = rdb_chain_active_joints_number(m_h);
+  }
+  ~Chain() { rdb_chain_destroy(m_h); }
+  Chain(const Chain&) = delete;
+  Chain& operator=(const Chain&) = delete;
+
+  unsigned int getLinksNumber() const { return m_nl; }
+  unsigned int getJointsNumber() const { return m_nj; }
+  unsigned int getActiveJointsNumber() const { return m_n; }
+  const rdb_chain* handle() const { return m_h; }
+  std::array<double, 3> getGravity() const
+  {
+    std::array<double, 3> g{};
+    rdb_chain_gravity(m_h, g.data());
+    return g;
+  }
+  VectorXd getNominalParameters() const
+  {
+    VectorXd p(10 * m_nj);
+    rdb_chain_nominal_parameters(m_h, p.data());
+    return p;
+  }
+  // Chain::setInputJointsName by chain-joint index (primitives_impl.h:705-742)
+  bool setInputJoints(const std::vector<int32_t>& chain_joint_of_input)
+  {
+    check(rdb_chain_set_input_joints(m_h, (int32_t)chain_joint_of_input.size(), chain_joint_of_input.data()));
+    m_n = rdb_chain_active_joints_number(m_h);
+    for (int32_t j : chain_joint_of_input)
+      if (j < 0 || j >= (int32_t)m_nj) return false;
+    return true;
+  }
+
+  // ---------------------------------------------------------------- per-sample getters (reference names)
+  Affine3dImage getTransformation(const VectorXd& q) { return toAffine(kin1(q, nullptr, nullptr, nullptr, &rdb_kinematics_out::T_tool, 12).data()); }
+  std::vector<Affine3dImage> getTransformations(const VectorXd& q)
+  {
+    const VectorXd t = kin1(q, nullptr, nullptr, nullptr, &rdb_kinematics_out::T_links, 12 * m_nl);
+    std::vector<Affine3dImage> out(m_nl);
+    for (unsigned l = 0; l < m_nl; l++) out[l] = toAffine(t.data() + 12 * l);
+    return out;
+  }
+  // 6 x n_act, column-major
+  VectorXd getJacobian(const VectorXd& q) { return kin1(q, nullptr, nullptr, nullptr, &rdb_kinematics_out::jacobian, 6 * m_n); }
+  std::vector<Vector6d> getTwist(const VectorXd& q, const VectorXd& Dq) { return six(kin1(q, &Dq, nullptr, nullptr, &rdb_kinematics_out::twist, 6 * m_nl)); }
+  Vector6d getTwistTool(const VectorXd& q, const VectorXd& Dq) { return getTwist(q, Dq).back(); }
+  std::vector<Vector6d> getDTwist(const VectorXd& q, const VectorXd& Dq, const VectorXd& DDq)
+  {
+    return six(kin1(q, &Dq, &DDq, nullptr, &rdb_kinematics_out::dtwist, 6 * m_nl));
+  }
+  Vector6d getDTwistTool(const VectorXd& q, const VectorXd& Dq, const VectorXd& DDq) { return getDTwist(q, Dq, DDq).back(); }
+  std::vector<Vector6d> getDTwistLinearPart(const VectorXd& q, const VectorXd& DDq)
+  {
+    return six(kin1(q, nullptr, &DDq, nullptr, &rdb_kinematics_out::dtwist_lin, 6 * m_nl));
+  }
+  std::vector<Vector6d> getDTwistNonLinearPart(const VectorXd& q, const VectorXd& Dq)
+  {
+    return six(kin1(q, &Dq, nullptr, nullptr, &rdb_kinematics_out::dtwist_nonlin, 6 * m_nl));
+  }
+  std::vector<Vector6d> getDDTwist(const VectorXd& q, const VectorXd& Dq, const VectorXd& DDq, const VectorXd& DDDq)
+  {
+    return six(kin1(q, &Dq, &DDq, &DDDq, &rdb_kinematics_out::ddtwist, 6 * m_nl));
+  }
+  Vector6d getDDTwistTool(const VectorXd& q, const VectorXd& Dq, const VectorXd& DDq, const VectorXd& DDDq)
+  {
+    return getDDTwist(q, Dq, DDq, DDDq).back();
+  }
+  std::vector<Vector6d> getDDTwistLinearPart(const VectorXd& q, const VectorXd& DDDq)
+  {
+    return six(kin1(q, nullptr, nullptr, &DDDq, &rdb_kinematics_out::ddtwist_lin, 6 * m_nl));
+  }
+  std::vector<Vector6d> getDDTwistNonLinearPart(const VectorXd& q, const VectorXd& Dq, const VectorXd& DDq)
+  {
+    return six(kin1(q, &Dq, &DDq, nullptr, &rdb_kinematics_out::ddtwist_nonlin, 6 * m_nl));
+  }
+  VectorXd getJointTorque(const VectorXd& q, const VectorXd& Dq, const VectorXd& DDq)
+  {
+    sizes(q, &Dq, &DDq, nullptr);
+    VectorXd tau(m_n);
+    rdb_samples in{1, 1, q.data(), Dq.data(), DDq.data(), nullptr};
+    check(rdb_torque_batch_host(m_h, &in, tau.data(), 1));
+    return tau;
+  }
+  VectorXd getJointTorqueNonLinearPart(const VectorXd& q, const VectorXd& Dq)
+  {
+    sizes(q, &Dq, nullptr, nullptr);
+    VectorXd tau(m_n);
+    rdb_samples in{1, 1, q.data(), Dq.data(), nullptr, nullptr};
+    check(rdb_torque_batch_host(m_h, &in, tau.data(), 1));
+    return tau;
+  }
+  // n_act x 10 nJ, column-major (the memory image of the Eigen::MatrixXd the reference returns by value)
+  VectorXd getRegressor(const VectorXd& q, const VectorXd& Dq, const VectorXd& DDq)
+  {
+    if (q.size() != Dq.size() || Dq.size() != DDq.size() || q.size() != m_n) throw std::invalid_argument("Input data dimensions mismatch");
+    VectorXd phi((size_t)10 * m_nj * m_n);
+    rdb_samples in{1, 1, q.data(), Dq.data(), DDq.data(), nullptr};
+    check(rdb_regressor_batch_host(m_h, &in, phi.data(), nullptr, 1));
+    return phi;
+  }
+  // n_act x n_act, column-major
+  VectorXd getJointInertia(const VectorXd& q)
+  {
+    sizes(q, nullptr, nullptr, nullptr);
+    VectorXd M((size_t)m_n * m_n);
+    rdb_samples in{1, 1, q.data(), nullptr, nullptr, nullptr};
+    check(rdb_inertia_batch_host(m_h, &in, M.data(), 1));
+    return M;
+  }
+
+  // ---------------------------------------------------------------- batched siblings (SoA planes, see rosdyn_b200.h)
+  // device pointers, asynchronous on `stream` (a cudaStream_t)
+  void computeTransformations(const rdb_samples& in, const rdb_kinematics_out& out, void* stream = nullptr) { check(rdb_kinematics_batch(m_h, &in, &out, stream)); }
+  void getJointTorque(const rdb_samples& in, double* torque, int64_t ld_out, void* stream = nullptr) { check(rdb_torque_batch(m_h, &in, torque, ld_out, stream)); }
+  void getRegressor(const rdb_samples& in, double* phi, double* torque, int64_t ld_out, void* stream = nullptr)
+  {
+    check(rdb_regressor_batch(m_h, &in, phi, torque, ld_out, stream));
+  }
+  void getJointInertia(const rdb_samples& in, double* inertia, int64_t ld_out, void* stream = nullptr) { check(rdb_inertia_batch(m_h, &in, inertia, ld_out, stream)); }
+  void getRegressorGram(const rdb_samples& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq, bool accumulate, void* stream = nullptr)
+  {
+    check(rdb_regressor_gram_batch(m_h, &in, tau_meas, gram, rhs, tau_sq, accumulate ? 1 : 0, stream));
+  }
+  // host pointers (copies and synchronisation inside)
+  void computeTransformationsHost(const rdb_samples& in, const rdb_kinematics_out& out) { check(rdb_kinematics_batch_host(m_h, &in, &out)); }
+  void getJointTorqueHost(const rdb_samples& in, double* torque, int64_t ld_out) { check(rdb_torque_batch_host(m_h, &in, torque, ld_out)); }
+  void getRegressorHost(const rdb_samples& in, double* phi, double* torque, int64_t ld_out) { check(rdb_regressor_batch_host(m_h, &in, phi, torque, ld_out)); }
+  void getJointInertiaHost(const rdb_samples& in, double* inertia, int64_t ld_out) { check(rdb_inertia_batch_host(m_h, &in, inertia, ld_out)); }
+  void getRegressorGramHost(const rdb_samples& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq, bool accumulate)
+  {
+    check(rdb_regressor_gram_batch_host(m_h, &in, tau_meas, gram, rhs, tau_sq, accumulate ? 1 : 0));
+  }
+
+#ifdef ROSDYN_B200_HAVE_EIGEN
+  // Eigen-typed drop-ins for the dynamics getters (same signatures as the reference)
+  Eigen::VectorXd getJointTorque(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq, const Eigen::VectorXd& DDq)
+  {
+    const VectorXd t = getJointTorque(VectorXd(q.data(), q.data() + q.size()), VectorXd(Dq.data(), Dq.data() + Dq.size()),
+                                      VectorXd(DDq.data(), DDq.data() + DDq.size()));
+    return Eigen::Map<const Eigen::VectorXd>(t.data(), t.size());
+  }
+  Eigen::MatrixXd getRegressor(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq, const Eigen::VectorXd& DDq)
+  {
+    const VectorXd p = getRegressor(VectorXd(q.data(), q.data() + q.size()), VectorXd(Dq.data(), Dq.data() + Dq.size()),
+                                    VectorXd(DDq.data(), DDq.data() + DDq.size()));
+    return Eigen::Map<const Eigen::MatrixXd>(p.data(), m_n, 10 * m_nj);
+  }
+  Eigen::MatrixXd getJointInertia(const Eigen::VectorXd& q)
+  {
+    const VectorXd M = getJointInertia(VectorXd(q.data(), q.data() + q.size()));
+    return Eigen::Map<const Eigen::MatrixXd>(M.data(), m_n, m_n);
+  }
+#endif
+
+private:
+  rdb_chain* m_h = nullptr;
+  unsigned int m_nj = 0, m_nl = 0, m_n = 0;
+
+  static void check(rdb_status s)
+  {
+    if (s == RDB_OK) return;
+    if (s == RDB_ERR_DIM_MISMATCH || s == RDB_ERR_INVALID_ARG) throw std::invalid_argument(rdb_last_error());
+    throw std::runtime_error(std::string("rosdyn_b200: ") + rdb_last_error());
+  }
+  void sizes(const VectorXd& q, const VectorXd* a, const VectorXd* b, const VectorXd* c) const
+  {
+    if (q.size() != m_n || (a && a->size() != m_n) || (b && b->size() != m_n) || (c && c->size() != m_n))
+      throw std::invalid_argument("Input data dimensions mismatch");
+  }
+  VectorXd kin1(const VectorXd& q, const VectorXd* Dq, const VectorXd* DDq, const VectorXd* DDDq, double* rdb_kinematics_out::*field, size_t rows)
+  {
+    sizes(q, Dq, DDq, DDDq);
+    VectorXd out(rows);
+    rdb_samples in{1, 1, q.data(), Dq ? Dq->data() : nullptr, DDq ? DDq->data() : nullptr, DDDq ? DDDq->data() : nullptr};
+    rdb_kinematics_out o{};
+    o.ld = 1;
+    o.*field = out.data();
+    check(rdb_kinematics_batch_host(m_h, &in, &o));
+    return out;
+  }
+  static Affine3dImage toAffine(const double* t34)  // 3x4 row-major -> 4x4 column-major
+  {
+    Affine3dImage T{};
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 4; c++) T[4 * c + r] = t34[4 * r + c];
+    T[15] = 1.0;
+    return T;
+  }
+  static std::vector<Vector6d> six(const VectorXd& v)
+  {
+    std::vector<Vector6d> out(v.size() / 6);
+    for (size_t l = 0; l < out.size(); l++)
+      for (int k = 0; k < 6; k++) out[l][k] = v[6 * l + k];
+    return out;
+  }
+};
+
+}  // namespace rosdyn_b200
+
+#ifdef ROSDYN_B200_DROP_IN
+namespace rosdyn = rosdyn_b200;  // lets `rosdyn::Chain` in identification code name this class
+#endif
+
+#endif  // ROSDYN_B200_CHAIN_HPP

@@ -354,7 +354,7 @@ def fill_uniform(n_planes: int, n: int, seed: int, stream_id: int, device=None):
 def fp64_peak(kind: str = "dmma", reps: int = 5) -> float:
     """Own FP64 roofline denominator in TFLOP/s: 'dfma' (vector pipe) or 'dmma' (mma.sync m8n8k4 f64)."""
     v = ctypes.c_double()
-    check(_lib.load().rdb_fp64_peak(0 if kind == "dfma" else 1, reps, ctypes.byref(v)))
+    check(_lib.load().rdb_fp64_peak({"dfma": 0, "dmma": 1, "mixed": 2}[kind], reps, ctypes.byref(v)))
     return float(v.value)
 
 

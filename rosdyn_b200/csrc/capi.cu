@@ -231,6 +231,16 @@ void rdb_chain_destroy(rdb_chain* chain)
   if (chain->dev) cudaFree(chain->dev);
   if (chain->gram.partials) cudaFree(chain->gram.partials);
   if (chain->gram.fused_partials) cudaFree(chain->gram.fused_partials);
+  GramHostPipe& hp = chain->gram_host;
+  for (int k = 0; k < GramHostPipe::NSLOT; k++)
+  {
+    if (hp.stage[k]) cudaFree(hp.stage[k]);
+    if (hp.copied[k]) cudaEventDestroy(hp.copied[k]);
+    if (hp.freed[k]) cudaEventDestroy(hp.freed[k]);
+  }
+  if (hp.d_out) cudaFree(hp.d_out);
+  if (hp.copy) cudaStreamDestroy(hp.copy);
+  if (hp.comp) cudaStreamDestroy(hp.comp);
   delete chain;
 }
 
@@ -359,7 +369,7 @@ void rdb_fill_uniform_host(double* x, int32_t n_planes, int64_t n, int64_t ld, u
 
 rdb_status rdb_fp64_peak(int32_t kind, int32_t reps, double* tflops)
 {
-  if (!tflops || kind < 0 || kind > 1) return fail(RDB_ERR_INVALID_ARG, "fp64_peak: bad argument");
+  if (!tflops || kind < 0 || kind > 2) return fail(RDB_ERR_INVALID_ARG, "fp64_peak: bad argument");
   if (rdb_device_count() <= 0) return fail(RDB_ERR_NO_DEVICE, "no CUDA device");
   RDB_CUDA(fp64_peak(kind, reps, tflops));
   return RDB_OK;
@@ -546,75 +556,84 @@ rdb_status rdb_inertia_batch_host(const rdb_chain* chain, const rdb_samples* in,
 rdb_status rdb_regressor_gram_batch_host(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                          double* tau_sq, int32_t accumulate)
 {
+  // Streaming pipeline kept in the handle (streams, 3 staging slots, events): H2D of chunk k+1/k+2 on the copy
+  // stream overlaps the fused kernel of chunk k on the compute stream; only (P^2+P+1) doubles come back.
+  // One host call at a time per handle (the handle's workspace is not shared between threads).
   RDB_TRY(check_samples(chain, in, true));
-  if (!in->dq || !in->ddq) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
   if (!gram || !rhs) return fail(RDB_ERR_INVALID_ARG, "gram / rhs must not be null");
-  const int n_in = chain->host.n_in, P = 10 * chain->host.nj;
-  HostIn hi;
-  hi.bind(in, n_in);
-  Plane pt;
-  pt.h_in = tau_meas; pt.planes = tau_meas ? n_in : 0; pt.ld = in->ld;
-  HostPipe pipe;
-  RDB_TRY(pipe.init(in->n, 1 << 21, {&hi.q, &hi.dq, &hi.ddq, &hi.dddq, &pt}));
-  double* d_out = nullptr;  // gram | rhs | tau_sq
+  rdb_chain* ch = const_cast<rdb_chain*>(chain);
+  GramHostPipe& hp = ch->gram_host;
+  const int n_in = ch->host.n_in, P = 10 * ch->host.nj;
+  const int64_t chunk = 1 << 19;
   const size_t n_out = (size_t)P * P + P + 1;
-  RDB_CUDA(cudaMalloc(&d_out, n_out * sizeof(double)));
-  rdb_status s = RDB_OK;
-  cudaEvent_t done[2] = {nullptr, nullptr};
-  cudaStream_t acc = pipe.st[0];  // the accumulation is ordered on one stream; the other slot only stages copies
-  do
+  if (!hp.copy)
   {
-    if (accumulate)
+    RDB_CUDA(cudaStreamCreateWithFlags(&hp.copy, cudaStreamNonBlocking));
+    RDB_CUDA(cudaStreamCreateWithFlags(&hp.comp, cudaStreamNonBlocking));
+    for (int k = 0; k < GramHostPipe::NSLOT; k++)
     {
-      if (cudaMemcpyAsync(d_out, gram, sizeof(double) * P * P, cudaMemcpyHostToDevice, acc) != cudaSuccess ||
-          cudaMemcpyAsync(d_out + (size_t)P * P, rhs, sizeof(double) * P, cudaMemcpyHostToDevice, acc) != cudaSuccess ||
-          (tau_sq && cudaMemcpyAsync(d_out + (size_t)P * P + P, tau_sq, sizeof(double), cudaMemcpyHostToDevice, acc) != cudaSuccess))
-      {
-        s = cuda_fail(cudaGetLastError(), "gram_host upload");
-        break;
-      }
-      if (!tau_sq) cudaMemsetAsync(d_out + (size_t)P * P + P, 0, sizeof(double), acc);
+      RDB_CUDA(cudaEventCreateWithFlags(&hp.copied[k], cudaEventDisableTiming));
+      RDB_CUDA(cudaEventCreateWithFlags(&hp.freed[k], cudaEventDisableTiming));
     }
-    for (int k = 0; k < 2; k++) cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming);
-    int slot = 0;
-    bool first = true;
-    for (int64_t off = 0; off < in->n && s == RDB_OK; off += pipe.chunk, slot ^= 1)
+  }
+  if (hp.planes != n_in || !hp.stage[0])
+  {
+    for (int k = 0; k < GramHostPipe::NSLOT; k++)
     {
-      const int64_t len = std::min<int64_t>(pipe.chunk, in->n - off);
-      cudaStream_t cp = pipe.st[slot] ? pipe.st[slot] : pipe.st[0];
-      // staging buffer `slot` is free once the kernel that read it (two chunks ago) has finished
-      if (cp != acc) cudaStreamWaitEvent(cp, done[slot], 0);
-      const int sl = pipe.st[slot] ? slot : 0;
-      if ((s = pipe.h2d(hi.q, sl, off, len)) != RDB_OK) break;
-      if ((s = pipe.h2d(hi.dq, sl, off, len)) != RDB_OK) break;
-      if ((s = pipe.h2d(hi.ddq, sl, off, len)) != RDB_OK) break;
-      if ((s = pipe.h2d(pt, sl, off, len)) != RDB_OK) break;
-      cudaEvent_t copied;
-      cudaEventCreateWithFlags(&copied, cudaEventDisableTiming);
-      cudaEventRecord(copied, cp);
-      cudaStreamWaitEvent(acc, copied, 0);
-      cudaEventDestroy(copied);
-      rdb_samples v = hi.view(sl, len, pipe.chunk);
-      s = rdb_regressor_gram_batch(chain, &v, pt.d[sl], d_out, d_out + (size_t)P * P, d_out + (size_t)P * P + P, (accumulate || !first) ? 1 : 0, acc);
-      cudaEventRecord(done[slot], acc);
-      first = false;
+      if (hp.stage[k]) cudaFree(hp.stage[k]);
+      hp.stage[k] = nullptr;
+      RDB_CUDA(cudaMalloc(&hp.stage[k], sizeof(double) * 4 * (size_t)std::max(n_in, 1) * chunk));
     }
-    if (s != RDB_OK) break;
-    if (in->n == 0 && !accumulate) cudaMemsetAsync(d_out, 0, n_out * sizeof(double), acc);
-    if (cudaMemcpyAsync(gram, d_out, sizeof(double) * P * P, cudaMemcpyDeviceToHost, acc) != cudaSuccess ||
-        cudaMemcpyAsync(rhs, d_out + (size_t)P * P, sizeof(double) * P, cudaMemcpyDeviceToHost, acc) != cudaSuccess ||
-        (tau_sq && cudaMemcpyAsync(tau_sq, d_out + (size_t)P * P + P, sizeof(double), cudaMemcpyDeviceToHost, acc) != cudaSuccess))
-    {
-      s = cuda_fail(cudaGetLastError(), "gram_host download");
-      break;
-    }
-    s = pipe.finish();
-  } while (0);
-  for (int k = 0; k < 2; k++)
-    if (done[k]) cudaEventDestroy(done[k]);
-  cudaDeviceSynchronize();
-  cudaFree(d_out);
-  return s;
+    if (hp.d_out) cudaFree(hp.d_out);
+    hp.d_out = nullptr;
+    RDB_CUDA(cudaMalloc(&hp.d_out, sizeof(double) * n_out));
+    hp.planes = n_in;
+    hp.n_out = n_out;
+  }
+  else if (hp.n_out < n_out)
+  {
+    cudaFree(hp.d_out);
+    hp.d_out = nullptr;
+    RDB_CUDA(cudaMalloc(&hp.d_out, sizeof(double) * n_out));
+    hp.n_out = n_out;
+  }
+  double* dG = hp.d_out;
+  double* db = dG + (size_t)P * P;
+  double* dt = db + P;
+  if (accumulate)
+  {
+    RDB_CUDA(cudaMemcpyAsync(dG, gram, sizeof(double) * P * P, cudaMemcpyHostToDevice, hp.comp));
+    RDB_CUDA(cudaMemcpyAsync(db, rhs, sizeof(double) * P, cudaMemcpyHostToDevice, hp.comp));
+    if (tau_sq) RDB_CUDA(cudaMemcpyAsync(dt, tau_sq, sizeof(double), cudaMemcpyHostToDevice, hp.comp));
+    else RDB_CUDA(cudaMemsetAsync(dt, 0, sizeof(double), hp.comp));
+  }
+  else if (in->n == 0)
+    RDB_CUDA(cudaMemsetAsync(dG, 0, sizeof(double) * n_out, hp.comp));
+  int64_t k = 0;
+  for (int64_t off = 0; off < in->n; off += chunk, k++)
+  {
+    const int slot = (int)(k % GramHostPipe::NSLOT);
+    const int64_t len = std::min<int64_t>(chunk, in->n - off);
+    if (k >= GramHostPipe::NSLOT) RDB_CUDA(cudaStreamWaitEvent(hp.copy, hp.freed[slot], 0));
+    double* base = hp.stage[slot];
+    const double* src[4] = {in->q, in->dq, in->ddq, tau_meas};
+    for (int a = 0; a < 4; a++)
+      if (src[a] && n_in > 0)
+        RDB_CUDA(cudaMemcpy2DAsync(base + (size_t)a * n_in * chunk, chunk * sizeof(double), src[a] + off, in->ld * sizeof(double),
+                                   len * sizeof(double), n_in, cudaMemcpyHostToDevice, hp.copy));
+    RDB_CUDA(cudaEventRecord(hp.copied[slot], hp.copy));
+    RDB_CUDA(cudaStreamWaitEvent(hp.comp, hp.copied[slot], 0));
+    rdb_samples v{len, chunk, base, base + (size_t)n_in * chunk, base + (size_t)2 * n_in * chunk, nullptr};
+    RDB_TRY(rdb_regressor_gram_batch(chain, &v, tau_meas ? base + (size_t)3 * n_in * chunk : nullptr, dG, db, dt, (accumulate || k > 0) ? 1 : 0,
+                                     hp.comp));
+    RDB_CUDA(cudaEventRecord(hp.freed[slot], hp.comp));
+  }
+  RDB_CUDA(cudaMemcpyAsync(gram, dG, sizeof(double) * P * P, cudaMemcpyDeviceToHost, hp.comp));
+  RDB_CUDA(cudaMemcpyAsync(rhs, db, sizeof(double) * P, cudaMemcpyDeviceToHost, hp.comp));
+  if (tau_sq) RDB_CUDA(cudaMemcpyAsync(tau_sq, dt, sizeof(double), cudaMemcpyDeviceToHost, hp.comp));
+  RDB_CUDA(cudaStreamSynchronize(hp.comp));
+  return RDB_OK;
 }
 
 }  // extern "C"

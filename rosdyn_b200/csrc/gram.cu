@@ -263,6 +263,31 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, 
   if (s == 12345.678) out[0] = s;
 }
 
+// both at once, independent accumulators: tells whether DFMA and DMMA share one FP64 datapath (sum ~= single peak) or not
+__global__ void __launch_bounds__(256) dmix_peak_kernel(double* out, int iters, double x)
+{
+  double c[8][2], a[16];
+#pragma unroll
+  for (int k = 0; k < 8; k++) c[k][0] = c[k][1] = threadIdx.x * 1e-3 + k;
+#pragma unroll
+  for (int k = 0; k < 16; k++) a[k] = threadIdx.x * 1e-3 + k;
+  const double fa = x, fb = 1.0 - x * 1e-12;
+  for (int it = 0; it < iters; it++)
+  {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+    {
+      dmma884(c[k][0], c[k][1], fa, fb);
+      a[2 * k] = fma(a[2 * k], x, 1e-9);
+      a[2 * k + 1] = fma(a[2 * k + 1], x, 1e-9);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += c[k][0] + c[k][1] + a[2 * k] + a[2 * k + 1];
+  if (s == 12345.678) out[0] = s;
+}
+
 cudaError_t fp64_peak(int kind, int reps, double* tflops)
 {
   int dev = 0, sms = 0;
@@ -280,7 +305,8 @@ cudaError_t fp64_peak(int kind, int reps, double* tflops)
   {
     cudaEventRecord(e0);
     if (kind == 0) dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999);
-    else dmma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999);
+    else if (kind == 1) dmma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999);
+    else dmix_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999);
     count_launch();
     cudaEventRecord(e1);
     e = cudaEventSynchronize(e1);
@@ -288,7 +314,9 @@ cudaError_t fp64_peak(int kind, int reps, double* tflops)
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     // DFMA: 2 flop per lane-instruction; DMMA m8n8k4: 2*8*8*4 = 512 flop per warp-instruction
-    const double flop = kind == 0 ? 2.0 * 16 * iters * (double)blocks * threads : 512.0 * 16 * iters * (double)blocks * (threads / 32);
+    const double flop = kind == 0   ? 2.0 * 16 * iters * (double)blocks * threads
+                        : kind == 1 ? 512.0 * 16 * iters * (double)blocks * (threads / 32)
+                                    : (512.0 * 8 * (threads / 32) + 2.0 * 16 * threads) * iters * (double)blocks;
     if (r > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
   }
   cudaEventDestroy(e0);

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "launch.h"
 #include "spatial.cuh"
@@ -54,18 +55,44 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramR
   const double keep = active ? 1.0 : 0.0;
   V3 U[NJ], S[NJ];
   double tau[NJ];
+  // all loads and all sin/cos first: they depend on nothing but the sample index, so their latency (DRAM, then the
+  // ~40-deep sincos dependency chains) overlaps across joints instead of serialising the walk
+  double qv[NJ], dqv[NJ], ddqv[NJ], sn[NJ], c1[NJ];
+#pragma unroll
+  for (int l = 0; l < NJ; l++)
+  {
+    qv[l] = ld_in(in.q, C.joint[l].in, in.ld, i);
+    dqv[l] = ld_in(in.dq, C.joint[l].in, in.ld, i);
+    ddqv[l] = ld_in(in.ddq, C.joint[l].in, in.ld, i);
+  }
+#pragma unroll
+  for (int l = 0; l < NJ; l++)
+  {
+    double sv = 0.0, cv = 1.0;
+    if (C.joint[l].type == RDB_JOINT_REVOLUTE) sincos(qv[l], &sv, &cv);
+    sn[l] = sv;
+    c1[l] = 1.0 - cv;
+  }
   V3 v = v3(0, 0, 0), w = v3(0, 0, 0), a = v3(0, 0, 0), al = v3(0, 0, 0);
   V3 g = v3(C.g);
 #pragma unroll
   for (int l = 0; l < NJ; l++)
   {
     const JointDev& J = C.joint[l];
-    const double ql = ld_in(in.q, J.in, in.ld, i);
-    const double dql = ld_in(in.dq, J.in, in.ld, i);
-    const double ddql = ld_in(in.ddq, J.in, in.ld, i);
+    const double dql = dqv[l], ddql = ddqv[l];
     double R[9];
-    V3 t;
-    joint_transform(J, ql, R, t);
+    V3 t = v3(J.t);
+    if (J.type == RDB_JOINT_REVOLUTE)
+    {
+#pragma unroll
+      for (int k = 0; k < 9; k++) R[k] = fma(c1[l], J.C[k], fma(sn[l], J.B[k], J.A[k]));
+    }
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < 9; k++) R[k] = J.A[k];
+      if (J.type == RDB_JOINT_PRISMATIC) t = axpy(t, v3(J.axp), qv[l]);
+    }
     const V3 axj = v3(J.ax);
     const V3 su = (J.type == RDB_JOINT_PRISMATIC) ? axj : v3(0, 0, 0);
     const V3 ss = (J.type == RDB_JOINT_REVOLUTE) ? axj : v3(0, 0, 0);
@@ -190,7 +217,7 @@ __device__ __forceinline__ void gram_consume(const GramRows& rows, const double*
 template <int NJ>
 __global__ void __launch_bounds__(GF_THREADS, 1)
     gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const __grid_constant__ GramRows rows, const SamplesDev in,
-                      const double* __restrict__ tau_meas, double* __restrict__ partial)
+                      const double* __restrict__ tau_meas, double* __restrict__ partial, const int dbg)
 {
   using G = GramGeom<NJ>;
   extern __shared__ __align__(16) double smem[];
@@ -211,7 +238,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1)
       first = false;
       const int64_t i = grp * 32 + lane;
       const bool active = i < in.n;
-      gram_generate<NJ>(C, rows, in, tau_meas, slot, active ? i : in.n - 1, active, lane);
+      if (!(dbg & 1)) gram_generate<NJ>(C, rows, in, tau_meas, slot, active ? i : in.n - 1, active, lane);
       __threadfence_block();
       bar_arrive(GF_BAR_FULL + s, GF_BAR_COUNT);
     }
@@ -229,7 +256,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1)
       {
         if (base + s >= ngroups) break;
         bar_sync(GF_BAR_FULL + s, GF_BAR_COUNT);
-        gram_consume<NJ>(rows, smem + (size_t)s * rows.slot_doubles, warp, lane, acc);
+        if (!(dbg & 2)) gram_consume<NJ>(rows, smem + (size_t)s * rows.slot_doubles, warp, lane, acc);
         if (base + s + stride < ngroups) bar_arrive(GF_BAR_EMPTY + s, GF_BAR_COUNT);  // the generator will come back
       }
     }
@@ -321,6 +348,7 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const GramRows& rows, const Sa
     cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
   }
+  static const int dbg = [] { const char* e = getenv("RDB_GRAM_DEBUG"); return e ? atoi(e) : 0; }();  // 1: skip generation, 2: skip MMA (timing experiments only)
   const int64_t ngroups = (in.n + 31) / 32;
   const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + GF_GEN_WARPS - 1) / GF_GEN_WARPS);
   const size_t need = sizeof(double) * (size_t)ch.sm_count * G::NT * 64;
@@ -333,7 +361,7 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const GramRows& rows, const Sa
     if (e != cudaSuccess) return e;
     ch.gram.fused_bytes = need;
   }
-  gram_fused_kernel<NJ><<<grid, GF_THREADS, smem, st>>>(narrow_g<NJ>(ch.host), rows, in, tau_meas, ch.gram.fused_partials);
+  gram_fused_kernel<NJ><<<grid, GF_THREADS, smem, st>>>(narrow_g<NJ>(ch.host), rows, in, tau_meas, ch.gram.fused_partials, dbg);
   count_launch();
   gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, gram, rhs, tau_sq, accumulate);
   count_launch();

@@ -18,6 +18,18 @@ struct GramWorkspace
   size_t fused_bytes = 0;
 };
 
+// persistent pipeline of rdb_regressor_gram_batch_host (capi.cu)
+struct GramHostPipe
+{
+  static constexpr int NSLOT = 3;
+  cudaStream_t copy = nullptr, comp = nullptr;
+  double* stage[NSLOT] = {nullptr, nullptr, nullptr};  // q | dq | ddq | tau_meas planes of one chunk
+  cudaEvent_t copied[NSLOT] = {nullptr, nullptr, nullptr}, freed[NSLOT] = {nullptr, nullptr, nullptr};
+  double* d_out = nullptr;  // gram | rhs | tau_sq
+  size_t n_out = 0;
+  int planes = -1;
+};
+
 struct ChainHost
 {
   ChainDev<RDB_MAX_JOINTS> host;           // model constants, host copy
@@ -26,6 +38,7 @@ struct ChainHost
   bool inputs_cover_all = true;  // every input index is fed by a chain joint (else outputs are pre-zeroed)
   double nominal[10 * RDB_MAX_JOINTS];
   GramWorkspace gram;
+  GramHostPipe gram_host;
   int sm_count = 148;
 };
 
