@@ -163,8 +163,10 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": f"{args.chain}: getJointTorque + getRegressor per sample on the host CPU, {n} samples/step",
-                                        "chain": args.chain, "samples_per_step": n},
+        "data": "synthetic",
+        "config": {"workload": f"{d.name}: getRegressor (6x70) + getJointTorque per sample (the GPU arm's workload), evaluated by the CPU "
+                               f"restatement of the reference's Chain loop; bounded sample of {n} samples/step",
+                   "chain": d.name, "samples_per_step": n, "mode": args.workload},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n} samples/step x {args.steps} steps, oracle/rosdyn_oracle.c (plain-C restatement of primitives_impl.h), OpenMP"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
