@@ -8,7 +8,7 @@ import os
 from .descriptor import CChainDesc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librosdyn_b200.so")
+LIB_PATH = os.environ.get("RDB_LIB_PATH") or os.path.join(HERE, "librosdyn_b200.so")  # override: kernel A/B experiments only
 
 _dp = ctypes.c_void_p  # device or host pointer to double
 i32, i64, u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64

@@ -2,15 +2,15 @@
 //
 //   G (+)= sum_s Phi_s^T Phi_s ,  b (+)= sum_s Phi_s^T tau_s ,  tau_sq (+)= sum_s tau_s^T tau_s
 //
-// Phi never touches HBM.  Per CTA (1 per SM, 7 warps):
+// Phi never touches HBM.  Per CTA (1 per SM, 11 warps):
 //   * 3 generator warps: one thread walks the chain of one sample (same link-frame recursion as dyn_kernel,
 //     kernels.cu) and writes the augmented regressor rows [Phi_row | tau_row] of its 32 samples into one of
 //     three shared-memory slots (only the structurally non-zero columns, XOR-swizzled, conflict free);
-//   * 4 MMA warps: consume a slot as soon as it is full.  The contraction index k = (sample, joint row);
+//   * 8 MMA warps: consume a slot as soon as it is full.  The contraction index k = (sample, joint row);
 //     a k-step is 4 samples of one joint row, so the zero pattern of Phi (row of chain joint j is zero left
-//     of column 10 j) is known at compile time and whole 8x8 tiles are skipped.  Each warp owns every
-//     upper-triangular tile of the (P+1)x(P+1) augmented Gram matrix in registers (45 tiles for P = 70) and a
-//     quarter of the k-steps, so no accumulator ever leaves the register file before the kernel ends.
+//     of column 10 j) is known at compile time and whole 8x8 tiles are skipped.  The upper-triangular tiles of the
+//     (P+1)x(P+1) augmented Gram matrix (45 for P = 70) stay in registers for the whole kernel: the two MMA warps of
+//     an SM sub-partition split them by tile-row parity (25 + 20 tiles), the four sub-partitions split the k-steps.
 //     tcgen05 has no f64 kind: the FP64 tensor path of sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA).
 //   * slots cycle through named barriers (full/empty), generation and DMMA overlap on the same FP64 pipes.
 // Per-CTA partials are summed in a fixed order by gram_fused_reduce_kernel (bit-reproducible for a given n).
@@ -25,7 +25,12 @@
 namespace rdb
 {
 
-constexpr int GF_MMA_WARPS = 4;
+#ifndef GF_TSPLIT
+#define GF_TSPLIT 2
+#endif
+constexpr int GF_KSPLIT = 4;                       // MMA warps that share the k-steps of a slot (one per SM sub-partition)
+constexpr int GF_TS = GF_TSPLIT;                   // 1: each MMA warp owns all tiles; 2: two warps per sub-partition split the tile rows by parity
+constexpr int GF_MMA_WARPS = GF_KSPLIT * GF_TS;
 constexpr int GF_GEN_WARPS = 3;  // == number of slots
 constexpr int GF_THREADS = 32 * (GF_MMA_WARPS + GF_GEN_WARPS);
 constexpr int GF_BAR_FULL = 1;   // named barriers 1..3: slot full ; 4..6: slot empty (0 is __syncthreads)
@@ -55,23 +60,14 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramR
   const double keep = active ? 1.0 : 0.0;
   V3 U[NJ], S[NJ];
   double tau[NJ];
-  // all loads and all sin/cos first: they depend on nothing but the sample index, so their latency (DRAM, then the
-  // ~40-deep sincos dependency chains) overlaps across joints instead of serialising the walk
-  double qv[NJ], dqv[NJ], ddqv[NJ], sn[NJ], c1[NJ];
+  // all loads first: they depend on nothing but the sample index, so the DRAM latency is paid once, not once per joint
+  double qv[NJ], dqv[NJ], ddqv[NJ];
 #pragma unroll
   for (int l = 0; l < NJ; l++)
   {
     qv[l] = ld_in(in.q, C.joint[l].in, in.ld, i);
     dqv[l] = ld_in(in.dq, C.joint[l].in, in.ld, i);
     ddqv[l] = ld_in(in.ddq, C.joint[l].in, in.ld, i);
-  }
-#pragma unroll
-  for (int l = 0; l < NJ; l++)
-  {
-    double sv = 0.0, cv = 1.0;
-    if (C.joint[l].type == RDB_JOINT_REVOLUTE) sincos(qv[l], &sv, &cv);
-    sn[l] = sv;
-    c1[l] = 1.0 - cv;
   }
   V3 v = v3(0, 0, 0), w = v3(0, 0, 0), a = v3(0, 0, 0), al = v3(0, 0, 0);
   V3 g = v3(C.g);
@@ -84,8 +80,13 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramR
     V3 t = v3(J.t);
     if (J.type == RDB_JOINT_REVOLUTE)
     {
+      // sincos stays inside the walk on purpose: hoisting all of them to the top measured 12 % slower end to end (the
+      // branchy sincos bodies then run back to back instead of interleaving with the previous link's projections)
+      double sv, cv;
+      sincos(qv[l], &sv, &cv);
+      const double c1 = 1.0 - cv;
 #pragma unroll
-      for (int k = 0; k < 9; k++) R[k] = fma(c1[l], J.C[k], fma(sn[l], J.B[k], J.A[k]));
+      for (int k = 0; k < 9; k++) R[k] = fma(c1, J.C[k], fma(sv, J.B[k], J.A[k]));
     }
     else
     {
@@ -170,12 +171,28 @@ struct GramGeom
   static constexpr int T = (P + 1 + 7) / 8;       // tile columns of the augmented matrix
   static constexpr int NT = T * (T + 1) / 2;      // upper-triangular tiles
   __host__ __device__ static constexpr int tile(int I, int J) { return I * T - I * (I - 1) / 2 + (J - I); }
+  // tile rows owned by an MMA warp: all (TS == 1) or the rows of parity `par` (TS == 2)
+  __host__ __device__ static constexpr bool owns(int I, int ts, int par) { return ts == 1 || (I & 1) == par; }
+  __host__ __device__ static constexpr int ntiles(int ts, int par)
+  {
+    int n = 0;
+    for (int I = 0; I < T; I++)
+      if (owns(I, ts, par)) n += T - I;
+    return n;
+  }
+  __host__ __device__ static constexpr int local(int I, int J, int ts, int par)
+  {
+    int n = 0;
+    for (int K = 0; K < I; K++)
+      if (owns(K, ts, par)) n += T - K;
+    return n + (J - I);
+  }
 };
 
-// all k-steps of one slot that belong to MMA warp `mw`
-template <int NJ>
-__device__ __forceinline__ void gram_consume(const GramRows& rows, const double* __restrict__ slot, int mw, int lane,
-                                             double (&acc)[GramGeom<NJ>::NT][2])
+// the k-steps of one slot that belong to k-split index `ks`, for the tile rows this warp owns
+template <int NJ, int PAR>
+__device__ __forceinline__ void gram_consume(const GramRows& rows, const double* __restrict__ slot, int ks, int lane,
+                                             double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
 {
   using G = GramGeom<NJ>;
   constexpr int P = G::P, T = G::T;
@@ -190,9 +207,9 @@ __device__ __forceinline__ void gram_consume(const GramRows& rows, const double*
     const int I0 = c0 / 8;
     const double* rowp = slot + rb;
 #pragma unroll
-    for (int kk = 0; kk < 8 / GF_MMA_WARPS; kk++)
+    for (int kk = 0; kk < 8 / GF_KSPLIT; kk++)
     {
-      const int s = 4 * (mw + GF_MMA_WARPS * kk) + t;
+      const int s = 4 * (ks + GF_KSPLIT * kk) + t;
       double b[T];
 #pragma unroll
       for (int J = 0; J < T; J++)
@@ -206,11 +223,65 @@ __device__ __forceinline__ void gram_consume(const GramRows& rows, const double*
 #pragma unroll
       for (int I = 0; I < T; I++)
       {
-        if (I < I0) continue;
+        if (I < I0 || !G::owns(I, GF_TS, PAR)) continue;
 #pragma unroll
-        for (int J = I; J < T; J++) dmma884f(acc[G::tile(I, J)][0], acc[G::tile(I, J)][1], b[I], b[J]);
+        for (int J = I; J < T; J++) dmma884f(acc[G::local(I, J, GF_TS, PAR)][0], acc[G::local(I, J, GF_TS, PAR)][1], b[I], b[J]);
       }
     }
+  }
+}
+
+template <int NJ, int PAR>
+__device__ __forceinline__ void gram_mma_role(const GramRows& rows, const SamplesDev& in, double* smem, int ks, int lane, int dbg)
+{
+  using G = GramGeom<NJ>;
+  constexpr int NTP = G::ntiles(GF_TS, PAR);
+  double acc[NTP][2];
+#pragma unroll
+  for (int k = 0; k < NTP; k++) acc[k][0] = acc[k][1] = 0.0;
+  const int64_t ngroups = (in.n + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * GF_GEN_WARPS;
+  for (int64_t base = (int64_t)blockIdx.x * GF_GEN_WARPS; base < ngroups; base += stride)
+  {
+#pragma unroll 1
+    for (int s = 0; s < GF_GEN_WARPS; s++)
+    {
+      if (base + s >= ngroups) break;
+      bar_sync(GF_BAR_FULL + s, GF_BAR_COUNT);
+      if (!(dbg & 2)) gram_consume<NJ, PAR>(rows, smem + (size_t)s * rows.slot_doubles, ks, lane, acc);
+      if (base + s + stride < ngroups) bar_arrive(GF_BAR_EMPTY + s, GF_BAR_COUNT);  // the generator will come back
+    }
+  }
+  // fixed-order reduction over the k-split warps that own the same tiles, into shared memory (the slots are dead by now)
+  bar_sync(7, 32 * GF_MMA_WARPS);
+  const int g = lane >> 2, t = lane & 3;
+  for (int w = 0; w < GF_KSPLIT; w++)
+  {
+    if (ks == w)
+    {
+#pragma unroll
+      for (int I = 0; I < G::T; I++)
+      {
+        if (!G::owns(I, GF_TS, PAR)) continue;
+#pragma unroll
+        for (int J = I; J < G::T; J++)
+        {
+          double* o = smem + G::tile(I, J) * 64 + g * 8 + 2 * t;
+          const int k = G::local(I, J, GF_TS, PAR);
+          if (w == 0)
+          {
+            o[0] = acc[k][0];
+            o[1] = acc[k][1];
+          }
+          else
+          {
+            o[0] += acc[k][0];
+            o[1] += acc[k][1];
+          }
+        }
+      }
+    }
+    bar_sync(7, 32 * GF_MMA_WARPS);
   }
 }
 
@@ -226,10 +297,12 @@ __global__ void __launch_bounds__(GF_THREADS, 1)
   // group of (iteration it, CTA, slot s): g = (it*gridDim.x + blockIdx.x)*GF_GEN_WARPS + s
   const int64_t stride = (int64_t)gridDim.x * GF_GEN_WARPS;
 
-  if (warp >= GF_MMA_WARPS)
+  const bool is_gen = warp >= GF_MMA_WARPS;  // (putting the generators first instead changes nothing: measured)
+  const int gen_id = warp - GF_MMA_WARPS, mma_id = warp;
+  if (is_gen)
   {
     // ------------------------------------------------ generator warp of slot s
-    const int s = warp - GF_MMA_WARPS;
+    const int s = gen_id;
     double* slot = smem + (size_t)s * rows.slot_doubles;
     bool first = true;
     for (int64_t grp = (int64_t)blockIdx.x * GF_GEN_WARPS + s; grp < ngroups; grp += stride)
@@ -242,54 +315,14 @@ __global__ void __launch_bounds__(GF_THREADS, 1)
       __threadfence_block();
       bar_arrive(GF_BAR_FULL + s, GF_BAR_COUNT);
     }
+    return;
   }
-  else
-  {
-    // ------------------------------------------------ MMA warps
-    double acc[G::NT][2];
-#pragma unroll
-    for (int k = 0; k < G::NT; k++) acc[k][0] = acc[k][1] = 0.0;
-    for (int64_t base = (int64_t)blockIdx.x * GF_GEN_WARPS; base < ngroups; base += stride)
-    {
-#pragma unroll 1
-      for (int s = 0; s < GF_GEN_WARPS; s++)
-      {
-        if (base + s >= ngroups) break;
-        bar_sync(GF_BAR_FULL + s, GF_BAR_COUNT);
-        if (!(dbg & 2)) gram_consume<NJ>(rows, smem + (size_t)s * rows.slot_doubles, warp, lane, acc);
-        if (base + s + stride < ngroups) bar_arrive(GF_BAR_EMPTY + s, GF_BAR_COUNT);  // the generator will come back
-      }
-    }
-    // stash for the cross-warp reduction below (slots are dead after the final __syncthreads)
-    __syncwarp();
-    // fallthrough to the common epilogue with acc live
-    bar_sync(7, 32 * GF_MMA_WARPS);  // every MMA warp finished reading the slots
-    const int g = lane >> 2, t = lane & 3;
-    for (int w = 0; w < GF_MMA_WARPS; w++)
-    {
-      if (warp == w)
-      {
-#pragma unroll
-        for (int k = 0; k < G::NT; k++)
-        {
-          double* o = smem + k * 64 + g * 8 + 2 * t;
-          if (w == 0)
-          {
-            o[0] = acc[k][0];
-            o[1] = acc[k][1];
-          }
-          else
-          {
-            o[0] += acc[k][0];
-            o[1] += acc[k][1];
-          }
-        }
-      }
-      bar_sync(7, 32 * GF_MMA_WARPS);
-    }
-    double* out = partial + (size_t)blockIdx.x * G::NT * 64;
-    for (int k = threadIdx.x; k < G::NT * 64; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
-  }
+  // ------------------------------------------------ MMA warps: k-split index = warp % 4 (its SM sub-partition), tile-row parity = warp / 4
+  const int ks = mma_id % GF_KSPLIT;
+  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, 0>(rows, in, smem, ks, lane, dbg);
+  else gram_mma_role<NJ, 1>(rows, in, smem, ks, lane, dbg);
+  double* out = partial + (size_t)blockIdx.x * G::NT * 64;
+  for (int k = mma_id * 32 + lane; k < G::NT * 64; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
 }
 
 // fixed-order sum of the per-CTA partials -> gram (full symmetric, column-major), rhs, tau_sq
