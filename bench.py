@@ -85,7 +85,7 @@ class ClockSampler:
                     self.max_mhz = float(out[1])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._thr = threading.Thread(target=self._loop, daemon=True)
@@ -128,9 +128,16 @@ def cpu_run(chain_name: str, n: int, threads: int, reps: int = 1):
     return n / best, best
 
 
+def host_threads() -> int:
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so do not ask OpenMP)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(chain_name: str, seconds: float):
-    from oracle.oracle import OracleChain
-    threads = OracleChain.max_threads()
+    threads = host_threads()
     rate, _ = cpu_run(chain_name, 20000 * max(1, threads // 4), threads)       # calibration
     n = int(max(50_000, min(rate * seconds, 50_000_000)))
     rate, dt = cpu_run(chain_name, n, threads)
@@ -144,11 +151,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.oracle import OracleChain
-    threads = OracleChain.max_threads()
+    threads = host_threads()
     rate, _ = cpu_run(args.chain, 20000 * max(1, threads // 4), threads)
     n = int(max(20_000, min(rate * 4.0, 20_000_000)))                           # ~4 s per step
-    from oracle.oracle import fill_uniform
+    from oracle.oracle import OracleChain, fill_uniform
     from rosdyn_b200 import fixtures
     d = fixtures.by_name(args.chain)
     oc = OracleChain(d)
@@ -307,13 +313,13 @@ def main():
         ach = S * flop / (ms * 1e-3 / args.steps) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None, "traffic": None,
                 "peak_source": "own FP64 micro-benchmark on this GPU (max of DMMA m8n8k4 and DFMA); MEASURED_PEAKS.json has no FP64 figure",
-                "fp64_peaks_tflops": peaks64, "flop_per_sample": flop, "kernel": "gram_fused_kernel<7> (regressor generation + DMMA normal equations)"}
+                "fp64_peaks_tflops": peaks64, "flop_per_sample": flop, "kernel": f"gram_fused_kernel<{d.n_joints}> (regressor generation + DMMA normal equations)"}
     else:
         bytes_per_sample = 8 * (3 * n_in + P * n_in + n_in)          # 3552 B for C6
         ach = S * bytes_per_sample / (ms * 1e-3 / args.steps) / 1e9
         peak = float(peaks["hbm_gbs"])
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})", "bytes_per_sample": bytes_per_sample, "kernel": "dyn_kernel<7,3> (regressor+torque)"}
+                "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})", "bytes_per_sample": bytes_per_sample, "kernel": f"dyn_kernel<{d.n_joints},3> (regressor+torque)"}
 
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.chain, args.cpu_seconds)
@@ -321,8 +327,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": (f"{d.name}: getRegressor (6x70) + getJointTorque per sample, "
-                                    + ("fused into Phi^T Phi / Phi^T tau normal equations" if gram else "materialised as 426 SoA planes in HBM")),
+            "config": {"workload": (f"{d.name}: getRegressor ({n_in}x{P}) + getJointTorque per sample, "
+                                    + ("fused into Phi^T Phi / Phi^T tau normal equations" if gram else f"materialised as {P * n_in + n_in} SoA planes in HBM")),
                        "chain": d.name, "samples_per_step_per_gpu": S, "mode": args.workload,
                        "l2": "inputs (and outputs) per step are far larger than the 126 MB L2; no flush needed",
                        "parallelism": f"{world} x independent sample shards" + (" + NCCL all-reduce of the partials" if gram and world > 1 else "")},

@@ -25,6 +25,13 @@ namespace rdb
 {
 
 #define RDB_BLOCK 128
+#ifndef RDB_KIN_MINB
+#define RDB_KIN_MINB 4  // min CTAs/SM asked of ptxas (register cap 65536/(128*MINB) = 128): measured on B200, config 2 runs
+                        // 2.59 -> 3.20 G samples/s and the jerk walker 5.22 -> 5.51 vs. the uncapped 244-register build
+#endif
+#ifndef RDB_DYN_MINB
+#define RDB_DYN_MINB 4  // link-frame walker at <= 128 registers: materialised regressor 0.88 -> 0.91 (C6) / 0.92 -> 0.97 (C7) of HBM peak
+#endif
 
 template <int NJ_T>
 struct Cap
@@ -254,7 +261,7 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
 }
 
 template <int NJ, int MODE>
-__global__ void __launch_bounds__(RDB_BLOCK) dyn_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, double* __restrict__ phi,
+__global__ void __launch_bounds__(RDB_BLOCK, RDB_DYN_MINB) dyn_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, double* __restrict__ phi,
                                                         double* __restrict__ tau, double* __restrict__ M, int64_t ld_out)
 {
   const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
@@ -481,7 +488,7 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
 }
 
 template <int NJ, unsigned MASK>
-__global__ void __launch_bounds__(RDB_BLOCK) kin_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const KinOutDev o)
+__global__ void __launch_bounds__(RDB_BLOCK, RDB_KIN_MINB) kin_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const KinOutDev o)
 {
   const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
   if (i >= in.n) return;
