@@ -104,6 +104,27 @@ rdb_status rdb_chain_gravity(const rdb_chain* chain, double out[3]); /* Chain::g
 /* Chain::getNominalParameters (PI.h:1382-1391): out[10*n_joints], per link m, mcx,mcy,mcz, Ixx,Ixy,Ixz,Iyy,Iyz,Izz */
 rdb_status rdb_chain_nominal_parameters(const rdb_chain* chain, double* out);
 
+/* ---- URDF -> chain (replaces urdfdom + Link/Joint::fromUrdf + Chain::init, PI.h:50-149, 276-331, 580-703) ---- */
+/* The chain between base_link and tool_link of a URDF document, as the reference would extract it.  Owned by the
+ * library; `desc` and every array stay valid until rdb_urdf_chain_free.  Limits follow PI.h:85-143 (malformed-URDF
+ * defaults included); default inputs are the moveable joints base -> tool (PI.h:631-636, 700). */
+typedef struct rdb_urdf_chain
+{
+  rdb_chain_desc desc;
+  const char* const* joint_names; /* [n_joints]      */
+  const char* const* link_names;  /* [n_joints + 1]  */
+  const double* q_max;            /* [n_joints] per chain joint (0 for fixed joints) */
+  const double* q_min;
+  const double* dq_max;
+  const double* ddq_max;
+  const double* tau_max;
+} rdb_urdf_chain;
+/* RDB_ERR_NOT_FOUND + "Base link not found" / "Tool link not found" (PI.h:601-613); gravity NULL = zero (P.h:346). */
+rdb_status rdb_urdf_parse(const char* urdf_xml, const char* base_link, const char* tool_link, const double gravity[3], rdb_urdf_chain** out);
+void rdb_urdf_chain_free(rdb_urdf_chain* chain);
+/* rosdyn::createChain(model, base, tool, gravity) (PI.h:1518-1527): parse + rdb_chain_create. */
+rdb_status rdb_chain_from_urdf(const char* urdf_xml, const char* base_link, const char* tool_link, const double gravity[3], rdb_chain** out);
+
 /* ---- batched inputs ------------------------------------------------------------------------------ */
 typedef struct rdb_samples
 {

@@ -54,6 +54,17 @@ public:
     m_nl = rdb_chain_links_number(m_h);
     m_n = rdb_chain_active_joints_number(m_h);
   }
+  // Chain(robot_description, base_link_name, ee_link_name, gravity) (primitives.h:349-352); throws std::runtime_error
+  // ("Base link not found" / "Tool link not found", primitives_impl.h:498-501) like the reference
+  Chain(const std::string& robot_description, const std::string& base_link_name, const std::string& ee_link_name,
+        const std::array<double, 3>& gravity = {0.0, 0.0, 0.0})
+  {
+    const rdb_status s = rdb_chain_from_urdf(robot_description.c_str(), base_link_name.c_str(), ee_link_name.c_str(), gravity.data(), &m_h);
+    if (s != RDB_OK) throw std::runtime_error(rdb_last_error());
+    m_nj = rdb_chain_joints_number(m_h);
+    m_nl = rdb_chain_links_number(m_h);
+    m_n = rdb_chain_active_joints_number(m_h);
+  }
   ~Chain() { rdb_chain_destroy(m_h); }
   Chain(const Chain&) = delete;
   Chain& operator=(const Chain&) = delete;

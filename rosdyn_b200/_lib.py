@@ -26,6 +26,12 @@ class CKinematicsOut(ctypes.Structure):
     _fields_ = [("ld", i64)] + [(k, _dp) for k in KIN_FIELDS]
 
 
+class CUrdfChain(ctypes.Structure):
+    _fields_ = [("desc", CChainDesc), ("joint_names", ctypes.POINTER(ctypes.c_char_p)), ("link_names", ctypes.POINTER(ctypes.c_char_p)),
+                ("q_max", ctypes.POINTER(ctypes.c_double)), ("q_min", ctypes.POINTER(ctypes.c_double)), ("dq_max", ctypes.POINTER(ctypes.c_double)),
+                ("ddq_max", ctypes.POINTER(ctypes.c_double)), ("tau_max", ctypes.POINTER(ctypes.c_double))]
+
+
 # every symbol include/rosdyn_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "rdb_abi_version": (i32, []),
@@ -41,6 +47,9 @@ SYMBOLS = {
     "rdb_chain_active_joints_number": (i32, [ctypes.c_void_p]),
     "rdb_chain_gravity": (i32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "rdb_chain_nominal_parameters": (i32, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "rdb_urdf_parse": (i32, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.POINTER(CUrdfChain))]),
+    "rdb_urdf_chain_free": (None, [ctypes.POINTER(CUrdfChain)]),
+    "rdb_chain_from_urdf": (i32, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_void_p)]),
     "rdb_kinematics_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(CKinematicsOut), ctypes.c_void_p]),
     "rdb_torque_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, ctypes.c_void_p]),
     "rdb_regressor_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, i64, ctypes.c_void_p]),
@@ -88,6 +97,9 @@ def check(status: int) -> None:
         return
     lib = load()
     msg = lib.rdb_last_error().decode() or lib.rdb_status_string(status).decode()
+    if status == RDB_ERR_NOT_FOUND:
+        # Chain ctor: throw std::runtime_error("Base link not found" / "Tool link not found") (primitives_impl.h:498-501, 601-613)
+        raise LookupError(msg)
     if status == RDB_ERR_DIM_MISMATCH:
         # Chain::getRegressor throws std::invalid_argument("Input data dimensions mismatch") (primitives_impl.h:1299-1309)
         raise ValueError(msg)

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OBJDIR = os.path.join(ROOT, "build")
 LIB = os.path.join(HERE, "librosdyn_b200.so")
-SOURCES = ["kernels.cu", "gram.cu", "gram_fused.cu", "capi.cu"]
+SOURCES = ["kernels.cu", "gram.cu", "gram_fused.cu", "capi.cu", "urdf.cpp"]
 HEADERS = ["chain_dev.h", "spatial.cuh", "launch.h", os.path.join("..", "..", "include", "rosdyn_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs, jobs = [], []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJDIR, s.replace(".cu", ".o"))
+        obj = os.path.join(OBJDIR, os.path.splitext(s)[0] + ".o")
         objs.append(obj)
         if force or not _newer(obj, [src] + hdrs):
             cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=5) as ex:
         list(ex.map(run, jobs))
     if force or jobs or not _newer(LIB, objs):
         run([NVCC, "-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs)

@@ -53,6 +53,13 @@ class Chain:
         self.nL = self._lib.rdb_chain_links_number(self._h)
         self.n_in = self._lib.rdb_chain_active_joints_number(self._h)
 
+    @classmethod
+    def from_urdf(cls, urdf_xml: str, base_link: str, tool_link: str, gravity: Optional[Sequence[float]] = None) -> "Chain":
+        """Chain(robot_description, base_link_name, ee_link_name, gravity) of the reference (primitives.h:349-352), with the
+        library's own URDF loader; raises LookupError("Base link not found" / "Tool link not found")."""
+        from .urdf import chain_from_urdf
+        return cls(chain_from_urdf(urdf_xml, base_link, tool_link, gravity))
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
@@ -362,12 +369,18 @@ def kernel_launch_count() -> int:
     return int(_lib.load().rdb_kernel_launch_count())
 
 
-def createChain(desc: ChainDesc, gravity: Optional[Sequence[float]] = None) -> Optional[Chain]:
-    """rosdyn::createChain (primitives_impl.h:1518-1527): returns None instead of raising when the model is bad."""
-    if gravity is not None:
-        desc.gravity = tuple(gravity)
+def createChain(model, base_frame: Optional[str] = None, tool_frame: Optional[str] = None,
+                gravity: Optional[Sequence[float]] = None) -> Optional[Chain]:
+    """rosdyn::createChain(urdf_model, base_frame, tool_frame, gravity) (primitives_impl.h:1518-1527).  `model` is a URDF string
+    (with base/tool frames) or a ChainDesc; like the reference it returns None instead of raising when the chain cannot be built."""
     try:
-        return Chain(desc)
+        if isinstance(model, str):
+            return Chain.from_urdf(model, base_frame, tool_frame, gravity)
+        if gravity is not None:
+            model.gravity = tuple(gravity)
+        return Chain(model)
+    except (LookupError, ValueError):
+        return None
     except _lib.RosdynB200Error as e:
         if e.status == _lib.RDB_ERR_INVALID_ARG:
             return None

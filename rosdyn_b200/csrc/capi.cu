@@ -23,6 +23,7 @@ static rdb_status fail(rdb_status s, const std::string& what)
   t_err = what;
   return s;
 }
+rdb_status set_error(rdb_status s, const std::string& what) { return fail(s, what); }  // for urdf.cpp
 static rdb_status cuda_fail(cudaError_t e, const char* where)
 {
   return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? RDB_ERR_NO_DEVICE : RDB_ERR_CUDA,

@@ -223,6 +223,23 @@ def test_large_batch_invariants(chains, torch):
     assert float((torch.einsum("rcs,cs->rs", J, dq) - v).abs().max()) <= RTOL * max(1.0, float(v.abs().max()))
 
 
+def test_chain_from_urdf(chains, torch):
+    """createChain(urdf, base, tool, g) through the library's URDF loader == the hand-written fixture chain."""
+    import os
+    from conftest import GOLDEN_DIR
+    from rosdyn_b200.chain import Chain, createChain
+    urdf = open(os.path.join(GOLDEN_DIR, "ur10_like.urdf")).read()
+    ch = createChain(urdf, "base_link", "tool0", (0.0, 0.0, -9.806))
+    assert ch is not None and ch.getActiveJointsNumber() == 6 and ch.getLinksName()[-1] == "tool0"
+    assert createChain(urdf, "base_link", "no_such_link", (0, 0, 0)) is None      # reference: createChain returns null
+    with pytest.raises(LookupError, match="Tool link not found"):
+        Chain.from_urdf(urdf, "base_link", "no_such_link")
+    _, ref, _ = chains("c6")
+    q, dq, ddq, _ = _inputs(torch, 6, 1000, 31)
+    assert_close(_np(ch.getJointTorque(q, dq, ddq)), _np(ref.getJointTorque(q, dq, ddq)), "torque", 1e-13)
+    assert_close(_np(ch.getRegressor(q, dq, ddq)), _np(ref.getRegressor(q, dq, ddq)), "regressor", 1e-13)
+
+
 def test_cpp_facade(torch, tmp_path):
     """The C++ rosdyn::Chain facade over the C-ABI (include/rosdyn_b200/chain.hpp): build the example and run its self-checks."""
     import os
