@@ -31,11 +31,42 @@ namespace rdb
 constexpr int GF_KSPLIT = 4;                       // MMA warps that share the k-steps of a slot (one per SM sub-partition)
 constexpr int GF_TS = GF_TSPLIT;                   // 1: each MMA warp owns all tiles; 2: two warps per sub-partition split the tile rows by parity
 constexpr int GF_MMA_WARPS = GF_KSPLIT * GF_TS;
-constexpr int GF_GEN_WARPS = 3;  // == number of slots
-constexpr int GF_THREADS = 32 * (GF_MMA_WARPS + GF_GEN_WARPS);
-constexpr int GF_BAR_FULL = 1;   // named barriers 1..3: slot full ; 4..6: slot empty (0 is __syncthreads)
-constexpr int GF_BAR_EMPTY = 1 + GF_GEN_WARPS;
-constexpr int GF_BAR_COUNT = 32 + 32 * GF_MMA_WARPS;  // one generator warp + all MMA warps
+constexpr int GF_SLOTS = 3;      // 32-sample slots in shared memory (the 227 KB limit is what bounds the samples in flight)
+#ifndef GF_RSPLIT
+#define GF_RSPLIT 1
+#endif
+constexpr int GF_MAXG = 3;       // most row groups (generator warps) per slot
+constexpr int GF_BAR_REDUCE = 1;  // named barrier of the final k-split reduction (0 is __syncthreads)
+
+// Row groups.  The generator of a slot is latency bound (one warp per 32 samples, ~2.8 k dependent-ish DP instructions), and shared
+// memory allows only GF_SLOTS x 32 samples in flight, so the rows of Phi of one slot are split between NG generator warps: warp g walks
+// the whole chain but carries the unit twists of, projects on and stores only the chain joints [bound(g), bound(g+1)).  Each (slot, group)
+// has its own full/empty mbarrier pair, so a generator never waits for the other groups of its slot.
+__host__ __device__ constexpr int gf_groups(int NJ) { return NJ >= 4 ? GF_RSPLIT : 1; }
+__host__ __device__ constexpr int gf_pairs_before(int NJ, int b)  // (joint, link) pairs of the rows < b
+{
+  int c = 0;
+  for (int j = 0; j < b; j++) c += NJ - j;
+  return c;
+}
+__host__ __device__ constexpr int gf_bound(int NJ, int NG, int g)  // first chain joint of group g (nearest to an even split of the pairs)
+{
+  if (g <= 0) return 0;
+  if (g >= NG) return NJ;
+  const int total = gf_pairs_before(NJ, NJ);
+  int best = 1, bestd = 1 << 30;
+  for (int b = 1; b < NJ; b++)
+  {
+    int d = gf_pairs_before(NJ, b) * NG - total * g;
+    if (d < 0) d = -d;
+    if (d < bestd)
+    {
+      bestd = d;
+      best = b;
+    }
+  }
+  return best;
+}
 
 struct GramRows
 {
@@ -44,55 +75,125 @@ struct GramRows
 };
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void dmma884f(double& d0, double& d1, double a, double b)
 {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+// mbarriers in shared memory (one full / one empty per (slot, row group)); arrive = release.cta, wait = acquire.cta
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b)
+{
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
+{
+  asm volatile(
+      "{\n .reg .pred p;\n"
+      "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra D;\n bra W;\n"
+      "D:\n}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------- generator
-// One sample per lane: getRegressor (+ getJointTorque) of sample i written to the slot (zeros when !active).
-template <int NJ>
-__device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramRows& rows, const SamplesDev& in, const double* __restrict__ tau_meas,
-                                              double* __restrict__ slot, int64_t i, bool active, int lane)
+// sin and cos of NJ angles at once, branch free on the fast path (|q| <= 1e5: 3-term Cody-Waite reduction by pi/2 with exact FMA
+// products, then the fdlibm kernel polynomials on |r| <= pi/4; <= 1 ulp like the library), so that the whole walk of a sample is ONE
+// basic block and the scheduler can overlap the serial transform chain of link l+1 with the projections of link l.  Huge or
+// non-finite angles take the library sincos (Payne-Hanek) in a single, rarely executed branch.
+__device__ __forceinline__ void sincos_fast(double x, double& s, double& c)
 {
-  constexpr int P = 10 * NJ;
-  const double keep = active ? 1.0 : 0.0;
-  V3 U[NJ], S[NJ];
-  double tau[NJ];
-  // all loads first: they depend on nothing but the sample index, so the DRAM latency is paid once, not once per joint
-  double qv[NJ], dqv[NJ], ddqv[NJ];
+  const double j = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-j, 1.57079632679489655800e+00, x);
+  r = fma(-j, 6.12323399573676603587e-17, r);
+  r = fma(-j, -1.49738490485916983294e-33, r);  // pi/2 = hi + mid + lo (lo is negative)
+  const int q = (int)j;
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double sr = fma(z * r, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const double ss = (q & 1) ? cr : sr, cc = (q & 1) ? sr : cr;
+  s = (q & 2) ? -ss : ss;
+  c = ((q + 1) & 2) ? -cc : cc;
+}
+
+template <int NJ>
+struct GenIn
+{
+  double q[NJ], dq[NJ], ddq[NJ], sv[NJ], cv[NJ];
+};
+template <int NJ>
+__device__ __forceinline__ void gen_load(const ChainDev<NJ>& C, const SamplesDev& in, int64_t i, GenIn<NJ>& x)
+{
 #pragma unroll
   for (int l = 0; l < NJ; l++)
   {
-    qv[l] = ld_in(in.q, C.joint[l].in, in.ld, i);
-    dqv[l] = ld_in(in.dq, C.joint[l].in, in.ld, i);
-    ddqv[l] = ld_in(in.ddq, C.joint[l].in, in.ld, i);
+    x.q[l] = ld_in(in.q, C.joint[l].in, in.ld, i);
+    x.dq[l] = ld_in(in.dq, C.joint[l].in, in.ld, i);
+    x.ddq[l] = ld_in(in.ddq, C.joint[l].in, in.ld, i);
   }
+}
+
+template <int NJ>
+__device__ __forceinline__ void gen_trig(GenIn<NJ>& x)
+{
+  bool big = false;
+#pragma unroll
+  for (int l = 0; l < NJ; l++)
+  {
+    sincos_fast(x.q[l], x.sv[l], x.cv[l]);
+    big |= !(fabs(x.q[l]) <= 1.0e5);
+  }
+  if (big)
+  {
+#pragma unroll
+    for (int l = 0; l < NJ; l++) sincos(x.q[l], &x.sv[l], &x.cv[l]);
+  }
+}
+
+// One sample per lane: the rows [J0, J1) of getRegressor (+ getJointTorque) of sample i written to the slot.
+// The walk (getTwist / getDTwist moved to link axes) covers every link; unit twists are carried only for the joints of this group.
+template <int NJ, int J0, int J1>
+__device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramRows& rows, const GenIn<NJ>& x, const SamplesDev& in,
+                                              const double* __restrict__ tau_meas, double* __restrict__ slot, int64_t i, int lane)
+{
+  constexpr int P = 10 * NJ;
+  constexpr int NR = J1 - J0 > 0 ? J1 - J0 : 1;
+  V3 U[NR], S[NR];
+  double tau[NR];
   V3 v = v3(0, 0, 0), w = v3(0, 0, 0), a = v3(0, 0, 0), al = v3(0, 0, 0);
   V3 g = v3(C.g);
 #pragma unroll
   for (int l = 0; l < NJ; l++)
   {
     const JointDev& J = C.joint[l];
-    const double dql = dqv[l], ddql = ddqv[l];
+    const double dql = x.dq[l], ddql = x.ddq[l];
     double R[9];
     V3 t = v3(J.t);
     if (J.type == RDB_JOINT_REVOLUTE)
     {
-      // sincos stays inside the walk on purpose: hoisting all of them to the top measured 12 % slower end to end (the
-      // branchy sincos bodies then run back to back instead of interleaving with the previous link's projections)
-      double sv, cv;
-      sincos(qv[l], &sv, &cv);
-      const double c1 = 1.0 - cv;
+      const double c1 = 1.0 - x.cv[l];
 #pragma unroll
-      for (int k = 0; k < 9; k++) R[k] = fma(c1, J.C[k], fma(sv, J.B[k], J.A[k]));
+      for (int k = 0; k < 9; k++) R[k] = fma(c1, J.C[k], fma(x.sv[l], J.B[k], J.A[k]));
     }
     else
     {
 #pragma unroll
       for (int k = 0; k < 9; k++) R[k] = J.A[k];
-      if (J.type == RDB_JOINT_PRISMATIC) t = axpy(t, v3(J.axp), qv[l]);
+      if (J.type == RDB_JOINT_PRISMATIC) t = axpy(t, v3(J.axp), x.q[l]);
     }
     const V3 axj = v3(J.ax);
     const V3 su = (J.type == RDB_JOINT_PRISMATIC) ? axj : v3(0, 0, 0);
@@ -108,21 +209,27 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramR
     const V3 xa = cross(w, ss);
     a = axpy(axpy(a, xl, dql), su, ddql);
     al = axpy(axpy(al, xa, dql), ss, ddql);
+    if (l < J0) continue;  // the rows of this group have no entries in the column blocks of earlier links
 #pragma unroll
-    for (int j = 0; j < l; j++)
+    for (int j = J0; j < J1; j++)
+      if (j < l)
+      {
+        U[j - J0] = rotT(R, cross_add(U[j - J0], S[j - J0], t));
+        S[j - J0] = rotT(R, S[j - J0]);
+      }
+    if (l < J1)
     {
-      U[j] = rotT(R, cross_add(U[j], S[j], t));
-      S[j] = rotT(R, S[j]);
+      U[l - J0] = su;
+      S[l - J0] = ss;
+      tau[l - J0] = 0.0;
     }
-    U[l] = su;
-    S[l] = ss;
-    tau[l] = 0.0;
     const double* Pl = C.link[l].pi;
     const V3 fm = cross_add(a - g, w, v);
 #pragma unroll
-    for (int j = 0; j <= l; j++)
+    for (int j = J0; j < J1; j++)
     {
-      const V3 u = U[j], s = S[j];
+      if (j > l) continue;
+      const V3 u = U[j - J0], s = S[j - J0];
       const double e0 = dot(u, fm);
       const V3 wu = cross(w, u);
       const V3 h = cross_add(cross_add(cross(u, al), w, wu), fm, s);
@@ -138,28 +245,44 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramR
       e[7] = fma(s.y, al.y, rho.y * w.y);
       e[8] = fma(s.y, al.z, fma(s.z, al.y, fma(rho.y, w.z, rho.z * w.y)));
       e[9] = fma(s.z, al.z, rho.z * w.z);
-      double tj = tau[j];
+      // tau_j += Phi_{j,l,:} . pi_l in two independent chains
+      double t0 = tau[j - J0], t1 = e[1] * Pl[1];
 #pragma unroll
-      for (int p = 0; p < 10; p++) tj = fma(e[p], Pl[p], tj);
-      tau[j] = tj;
+      for (int p = 0; p < 10; p += 2) t0 = fma(e[p], Pl[p], t0);
+#pragma unroll
+      for (int p = 3; p < 10; p += 2) t1 = fma(e[p], Pl[p], t1);
+      tau[j - J0] = t0 + t1;
       const int rb = rows.base[j];
       if (rb >= 0)
       {
         double* o = slot + rb + (10 * (l - j)) * 32;
 #pragma unroll
-        for (int p = 0; p < 10; p++) o[p * 32 + (lane ^ (4 * ((10 * l + p) & 3)))] = e[p] * keep;
+        for (int p = 0; p < 10; p++) o[p * 32 + (lane ^ (4 * ((10 * l + p) & 3)))] = e[p];
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < NJ; j++)
+  for (int j = J0; j < J1; j++)
   {
     const int rb = rows.base[j];
     if (rb >= 0)
     {
-      const double tv = tau_meas ? __ldcs(tau_meas + (int64_t)C.joint[j].in * in.ld + i) : tau[j];
-      slot[rb + (P - 10 * j) * 32 + (lane ^ (4 * (P & 3)))] = tv * keep;
+      const double tv = tau_meas ? __ldcs(tau_meas + (int64_t)C.joint[j].in * in.ld + i) : tau[j - J0];
+      slot[rb + (P - 10 * j) * 32 + (lane ^ (4 * (P & 3)))] = tv;
     }
+  }
+}
+
+// lanes past the end of the batch (last group only): their rows of the group [J0, J1) become exact zeros
+template <int NJ, int J0, int J1>
+__device__ __noinline__ void gram_zero_lane(const GramRows& rows, double* __restrict__ slot, int lane)
+{
+  constexpr int P = 10 * NJ;
+  for (int j = J0; j < J1; j++)
+  {
+    const int rb = rows.base[j];
+    if (rb < 0) continue;
+    for (int c = 10 * j; c <= P; c++) slot[rb + (c - 10 * j) * 32 + (lane ^ (4 * (c & 3)))] = 0.0;
   }
 }
 
@@ -170,6 +293,8 @@ struct GramGeom
   static constexpr int P = 10 * NJ;
   static constexpr int T = (P + 1 + 7) / 8;       // tile columns of the augmented matrix
   static constexpr int NT = T * (T + 1) / 2;      // upper-triangular tiles
+  static constexpr int NG = gf_groups(NJ);        // row groups = generator warps per slot
+  static constexpr int THREADS = 32 * (GF_MMA_WARPS + GF_SLOTS * NG);
   __host__ __device__ static constexpr int tile(int I, int J) { return I * T - I * (I - 1) / 2 + (J - I); }
   // tile rows owned by an MMA warp: all (TS == 1) or the rows of parity `par` (TS == 2)
   __host__ __device__ static constexpr bool owns(int I, int ts, int par) { return ts == 1 || (I & 1) == par; }
@@ -189,8 +314,8 @@ struct GramGeom
   }
 };
 
-// the k-steps of one slot that belong to k-split index `ks`, for the tile rows this warp owns
-template <int NJ, int PAR>
+// the k-steps of the rows [J0, J1) of one slot that belong to k-split index `ks`, for the tile rows this warp owns
+template <int NJ, int PAR, int J0, int J1>
 __device__ __forceinline__ void gram_consume(const GramRows& rows, const double* __restrict__ slot, int ks, int lane,
                                              double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
 {
@@ -199,7 +324,7 @@ __device__ __forceinline__ void gram_consume(const GramRows& rows, const double*
   const int g = lane >> 2, t = lane & 3;
   const int swz = 4 * (g & 3);
 #pragma unroll
-  for (int j = 0; j < NJ; j++)
+  for (int j = J0; j < J1; j++)
   {
     const int rb = rows.base[j];
     if (rb < 0) continue;
@@ -231,8 +356,31 @@ __device__ __forceinline__ void gram_consume(const GramRows& rows, const double*
   }
 }
 
+struct GramBars
+{
+  uint64_t full[GF_SLOTS][GF_MAXG], empty[GF_SLOTS][GF_MAXG];
+};
+
+template <int NJ, int PAR, int GRP>
+__device__ __forceinline__ void gram_consume_groups(const GramRows& rows, const double* slot, GramBars* bars, int s, uint32_t parity, bool again,
+                                                    int ks, int lane, int dbg, double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
+{
+  using G = GramGeom<NJ>;
+  if constexpr (GRP < G::NG)
+  {
+    mbar_wait(&bars->full[s][GRP], parity);
+    if (!(dbg & 2)) gram_consume<NJ, PAR, gf_bound(NJ, G::NG, GRP), gf_bound(NJ, G::NG, GRP + 1)>(rows, slot, ks, lane, acc);
+    if (again)  // the generator will come back for this slot
+    {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->empty[s][GRP]);
+    }
+    gram_consume_groups<NJ, PAR, GRP + 1>(rows, slot, bars, s, parity, again, ks, lane, dbg, acc);
+  }
+}
+
 template <int NJ, int PAR>
-__device__ __forceinline__ void gram_mma_role(const GramRows& rows, const SamplesDev& in, double* smem, int ks, int lane, int dbg)
+__device__ __forceinline__ void gram_mma_role(const GramRows& rows, const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane, int dbg)
 {
   using G = GramGeom<NJ>;
   constexpr int NTP = G::ntiles(GF_TS, PAR);
@@ -240,20 +388,19 @@ __device__ __forceinline__ void gram_mma_role(const GramRows& rows, const Sample
 #pragma unroll
   for (int k = 0; k < NTP; k++) acc[k][0] = acc[k][1] = 0.0;
   const int64_t ngroups = (in.n + 31) / 32;
-  const int64_t stride = (int64_t)gridDim.x * GF_GEN_WARPS;
-  for (int64_t base = (int64_t)blockIdx.x * GF_GEN_WARPS; base < ngroups; base += stride)
+  const int64_t stride = (int64_t)gridDim.x * GF_SLOTS;
+  uint32_t parity = 0;
+  for (int64_t base = (int64_t)blockIdx.x * GF_SLOTS; base < ngroups; base += stride, parity ^= 1)
   {
 #pragma unroll 1
-    for (int s = 0; s < GF_GEN_WARPS; s++)
+    for (int s = 0; s < GF_SLOTS; s++)
     {
       if (base + s >= ngroups) break;
-      bar_sync(GF_BAR_FULL + s, GF_BAR_COUNT);
-      if (!(dbg & 2)) gram_consume<NJ, PAR>(rows, smem + (size_t)s * rows.slot_doubles, ks, lane, acc);
-      if (base + s + stride < ngroups) bar_arrive(GF_BAR_EMPTY + s, GF_BAR_COUNT);  // the generator will come back
+      gram_consume_groups<NJ, PAR, 0>(rows, smem + (size_t)s * rows.slot_doubles, bars, s, parity, base + s + stride < ngroups, ks, lane, dbg, acc);
     }
   }
   // fixed-order reduction over the k-split warps that own the same tiles, into shared memory (the slots are dead by now)
-  bar_sync(7, 32 * GF_MMA_WARPS);
+  bar_sync(GF_BAR_REDUCE, 32 * GF_MMA_WARPS);
   const int g = lane >> 2, t = lane & 3;
   for (int w = 0; w < GF_KSPLIT; w++)
   {
@@ -281,46 +428,78 @@ __device__ __forceinline__ void gram_mma_role(const GramRows& rows, const Sample
         }
       }
     }
-    bar_sync(7, 32 * GF_MMA_WARPS);
+    bar_sync(GF_BAR_REDUCE, 32 * GF_MMA_WARPS);
+  }
+}
+
+template <int NJ, int GRP>
+__device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const GramRows& rows, const SamplesDev& in, const double* __restrict__ tau_meas,
+                                              double* smem, GramBars* bars, int gen_id, int lane, int dbg)
+{
+  using G = GramGeom<NJ>;
+  if constexpr (GRP < G::NG)
+  {
+    if (gen_id % G::NG == GRP)
+    {
+      const int s = gen_id / G::NG;
+      double* slot = smem + (size_t)s * rows.slot_doubles;
+      const int64_t ngroups = (in.n + 31) / 32;
+      const int64_t stride = (int64_t)gridDim.x * GF_SLOTS;
+      constexpr int J0 = gf_bound(NJ, G::NG, GRP), J1 = gf_bound(NJ, G::NG, GRP + 1);
+      uint32_t parity = 1;  // first wait on an un-arrived barrier with parity 1 returns at once ("previous phase complete")
+      for (int64_t grp = (int64_t)blockIdx.x * GF_SLOTS + s; grp < ngroups; grp += stride, parity ^= 1)
+      {
+        // the inputs are requested BEFORE waiting for the slot: the DRAM latency hides behind the consumers' work on the previous group
+        const int64_t i = grp * 32 + lane;
+        GenIn<NJ> cur;
+        gen_load<NJ>(C, in, min(i, in.n - 1), cur);
+        gen_trig<NJ>(cur);
+        mbar_wait(&bars->empty[s][GRP], parity);  // consumers released this part of the slot
+        if (!(dbg & 1))
+        {
+          gram_generate<NJ, J0, J1>(C, rows, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
+          if (i >= in.n) gram_zero_lane<NJ, J0, J1>(rows, slot, lane);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->full[s][GRP]);
+      }
+    }
+    else
+      gram_gen_role<NJ, GRP + 1>(C, rows, in, tau_meas, smem, bars, gen_id, lane, dbg);
   }
 }
 
 template <int NJ>
-__global__ void __launch_bounds__(GF_THREADS, 1)
+__global__ void __launch_bounds__(GramGeom<NJ>::THREADS, 1)
     gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const __grid_constant__ GramRows rows, const SamplesDev in,
                       const double* __restrict__ tau_meas, double* __restrict__ partial, const int dbg)
 {
   using G = GramGeom<NJ>;
   extern __shared__ __align__(16) double smem[];
+  __shared__ GramBars bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ngroups = (in.n + 31) / 32;
-  // group of (iteration it, CTA, slot s): g = (it*gridDim.x + blockIdx.x)*GF_GEN_WARPS + s
-  const int64_t stride = (int64_t)gridDim.x * GF_GEN_WARPS;
-
-  const bool is_gen = warp >= GF_MMA_WARPS;  // (putting the generators first instead changes nothing: measured)
-  const int gen_id = warp - GF_MMA_WARPS, mma_id = warp;
-  if (is_gen)
+  if (threadIdx.x == 0)
   {
-    // ------------------------------------------------ generator warp of slot s
-    const int s = gen_id;
-    double* slot = smem + (size_t)s * rows.slot_doubles;
-    bool first = true;
-    for (int64_t grp = (int64_t)blockIdx.x * GF_GEN_WARPS + s; grp < ngroups; grp += stride)
-    {
-      if (!first) bar_sync(GF_BAR_EMPTY + s, GF_BAR_COUNT);  // consumers released the slot
-      first = false;
-      const int64_t i = grp * 32 + lane;
-      const bool active = i < in.n;
-      if (!(dbg & 1)) gram_generate<NJ>(C, rows, in, tau_meas, slot, active ? i : in.n - 1, active, lane);
-      __threadfence_block();
-      bar_arrive(GF_BAR_FULL + s, GF_BAR_COUNT);
-    }
+    for (int s = 0; s < GF_SLOTS; s++)
+      for (int g = 0; g < GF_MAXG; g++)
+      {
+        mbar_init(&bars.full[s][g], 1);             // lane 0 of the generator warp, after __syncwarp
+        mbar_init(&bars.empty[s][g], GF_MMA_WARPS);  // lane 0 of every MMA warp
+      }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // group of (iteration it, CTA, slot s): (it*gridDim.x + blockIdx.x)*GF_SLOTS + s ; generator warp (s, g) writes the rows of group g
+  if (warp >= GF_MMA_WARPS)
+  {
+    gram_gen_role<NJ, 0>(C, rows, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
     return;
   }
   // ------------------------------------------------ MMA warps: k-split index = warp % 4 (its SM sub-partition), tile-row parity = warp / 4
+  const int mma_id = warp;
   const int ks = mma_id % GF_KSPLIT;
-  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, 0>(rows, in, smem, ks, lane, dbg);
-  else gram_mma_role<NJ, 1>(rows, in, smem, ks, lane, dbg);
+  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, 0>(rows, in, smem, &bars, ks, lane, dbg);
+  else gram_mma_role<NJ, 1>(rows, in, smem, &bars, ks, lane, dbg);
   double* out = partial + (size_t)blockIdx.x * G::NT * 64;
   for (int k = mma_id * 32 + lane; k < G::NT * 64; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
 }
@@ -376,14 +555,14 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const GramRows& rows, const Sa
                                    double* tau_sq, int accumulate, cudaStream_t st)
 {
   using G = GramGeom<NJ>;
-  const size_t smem = sizeof(double) * (size_t)std::max(rows.slot_doubles * GF_GEN_WARPS, G::NT * 64);
+  const size_t smem = sizeof(double) * (size_t)std::max(rows.slot_doubles * GF_SLOTS, G::NT * 64);
   {
-    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   static const int dbg = [] { const char* e = getenv("RDB_GRAM_DEBUG"); return e ? atoi(e) : 0; }();  // 1: skip generation, 2: skip MMA (timing experiments only)
   const int64_t ngroups = (in.n + 31) / 32;
-  const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + GF_GEN_WARPS - 1) / GF_GEN_WARPS);
+  const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + GF_SLOTS - 1) / GF_SLOTS);
   const size_t need = sizeof(double) * (size_t)ch.sm_count * G::NT * 64;
   if (ch.gram.fused_bytes < need)
   {
@@ -394,7 +573,7 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const GramRows& rows, const Sa
     if (e != cudaSuccess) return e;
     ch.gram.fused_bytes = need;
   }
-  gram_fused_kernel<NJ><<<grid, GF_THREADS, smem, st>>>(narrow_g<NJ>(ch.host), rows, in, tau_meas, ch.gram.fused_partials, dbg);
+  gram_fused_kernel<NJ><<<grid, G::THREADS, smem, st>>>(narrow_g<NJ>(ch.host), rows, in, tau_meas, ch.gram.fused_partials, dbg);
   count_launch();
   gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, gram, rhs, tau_sq, accumulate);
   count_launch();
@@ -420,7 +599,7 @@ cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double*
     }
   }
   rows.slot_doubles = off;
-  if (off == 0 || sizeof(double) * (size_t)off * GF_GEN_WARPS > 227 * 1024) return cudaErrorNotSupported;
+  if (off == 0 || sizeof(double) * (size_t)off * GF_SLOTS + 1024 > 227 * 1024) return cudaErrorNotSupported;
   switch (nj)
   {
 #define X(N) \
