@@ -35,6 +35,9 @@ constexpr int GF_SLOTS = 3;      // 32-sample slots in shared memory (the 227 KB
 #ifndef GF_RSPLIT
 #define GF_RSPLIT 1
 #endif
+#ifndef GF_UNEVEN
+#define GF_UNEVEN 0  // 1: sub-partition 3 (no generator warp) takes 3 of the 8 k-steps -- measured much slower (it becomes the critical path)
+#endif
 constexpr int GF_MAXG = 3;       // most row groups (generator warps) per slot
 constexpr int GF_BAR_REDUCE = 1;  // named barrier of the final k-split reduction (0 is __syncthreads)
 
@@ -316,7 +319,7 @@ struct GramGeom
 
 // the k-steps of the rows [J0, J1) of one slot that belong to k-split index `ks`, for the tile rows this warp owns
 template <int NJ, int PAR, int J0, int J1>
-__device__ __forceinline__ void gram_consume(const GramRows& rows, const double* __restrict__ slot, int ks, int lane,
+__device__ __forceinline__ void gram_consume(const GramRows& rows, const double* __restrict__ slot, int k0, int k1, int lane,
                                              double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
 {
   using G = GramGeom<NJ>;
@@ -331,10 +334,10 @@ __device__ __forceinline__ void gram_consume(const GramRows& rows, const double*
     const int c0 = 10 * j;
     const int I0 = c0 / 8;
     const double* rowp = slot + rb;
-#pragma unroll
-    for (int kk = 0; kk < 8 / GF_KSPLIT; kk++)
+#pragma unroll 1
+    for (int kk = k0; kk < k1; kk++)
     {
-      const int s = 4 * (ks + GF_KSPLIT * kk) + t;
+      const int s = 4 * kk + t;
       double b[T];
 #pragma unroll
       for (int J = 0; J < T; J++)
@@ -369,7 +372,21 @@ __device__ __forceinline__ void gram_consume_groups(const GramRows& rows, const 
   if constexpr (GRP < G::NG)
   {
     mbar_wait(&bars->full[s][GRP], parity);
-    if (!(dbg & 2)) gram_consume<NJ, PAR, gf_bound(NJ, G::NG, GRP), gf_bound(NJ, G::NG, GRP + 1)>(rows, slot, ks, lane, acc);
+    // k-steps (4 samples each) of this warp in this slot.  The generator warps sit on SM sub-partitions 0..2 and share the FP64 datapath
+    // with the MMA warps there, sub-partition 3 has MMA warps only: it takes 3 of the 8 k-steps, the others 2, 2 and 1 (rotating with the slot)
+    int k0, k1;
+    if (GF_UNEVEN && GF_SLOTS == 3 && GF_KSPLIT == 4)
+    {
+      const int o = ks == 3 ? 3 : (ks - s + 3) % 3;
+      k0 = o == 3 ? 0 : (o == 0 ? 3 : (o == 1 ? 5 : 7));
+      k1 = o == 3 ? 3 : (o == 0 ? 5 : (o == 1 ? 7 : 8));
+    }
+    else
+    {
+      k0 = ks * (8 / GF_KSPLIT);
+      k1 = k0 + 8 / GF_KSPLIT;
+    }
+    if (!(dbg & 2)) gram_consume<NJ, PAR, gf_bound(NJ, G::NG, GRP), gf_bound(NJ, G::NG, GRP + 1)>(rows, slot, k0, k1, lane, acc);
     if (again)  // the generator will come back for this slot
     {
       __syncwarp();
