@@ -28,12 +28,39 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(_dbl_p)
 
 
+REF_LIB = os.path.join(_HERE, "_ref", "librosdyn_ref.so")
+REFERENCE_ROOT = "/root/reference/rosdyn_core/include"
+
+
+def build_ref(force: bool = False) -> bool:
+    """Compile the REFERENCE's own headers (where they lie under /root/reference) against the stand-in third-party headers of
+    oracle/shim/ into oracle/_ref/librosdyn_ref.so.  Returns False when the reference tree is absent (the GPU box only uses
+    the prebuilt file)."""
+    if not os.path.isdir(REFERENCE_ROOT):
+        return os.path.exists(REF_LIB)
+    deps = [os.path.join(_HERE, "ref_driver.cpp"), os.path.join(_HERE, "shim", "mini_eigen.h")]
+    if force or not os.path.exists(REF_LIB) or any(os.path.getmtime(REF_LIB) < os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return True
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_LIB)
+
+
 class _Lib:
-    def __init__(self, fast: bool = False):
-        name = "librosdyn_oracle_fast.so" if fast else "librosdyn_oracle.so"
-        path = os.path.join(_HERE, name)
-        if not os.path.exists(path):
-            build()
+    def __init__(self, fast=False):
+        """fast: False = restatement (-O3), True = restatement with the reference's -Ofast test flags, "ref" = the reference's own
+        headers compiled against oracle/shim (oracle/_ref/librosdyn_ref.so)."""
+        if fast == "ref":
+            path = REF_LIB
+            if not os.path.exists(path) and not build_ref():
+                raise FileNotFoundError(path)
+        else:
+            name = "librosdyn_oracle_fast.so" if fast else "librosdyn_oracle.so"
+            path = os.path.join(_HERE, name)
+            if not os.path.exists(path):
+                build()
         self.lib = ctypes.CDLL(path)
         L = self.lib
         L.oracle_chain_create.restype = ctypes.c_void_p
@@ -47,13 +74,14 @@ class _Lib:
         L.oracle_regressor_torque_batch.argtypes = [vp, i64, i64, _dbl_p, _dbl_p, _dbl_p, i64, _dbl_p, _dbl_p, ci]
         L.oracle_inertia_batch.argtypes = [vp, i64, i64, _dbl_p, i64, _dbl_p, ci]
         L.oracle_regressor_gram.argtypes = [vp, i64, i64, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p, _dbl_p]
-        L.oracle_fill_uniform.argtypes = [_dbl_p, ci, i64, i64, ctypes.c_uint64, ci]
+        if fast != "ref":
+            L.oracle_fill_uniform.argtypes = [_dbl_p, ci, i64, i64, ctypes.c_uint64, ci]
 
 
 _libs = {}
 
 
-def lib(fast: bool = False) -> _Lib:
+def lib(fast=False) -> _Lib:
     if fast not in _libs:
         _libs[fast] = _Lib(fast)
     return _libs[fast]
@@ -74,12 +102,13 @@ def _c(a, rows=None):
 
 
 class OracleChain:
-    """CPU restatement of rosdyn::Chain, batched over SoA arrays x[component][N] (same layout as the C-ABI)."""
+    """CPU restatement of rosdyn::Chain, batched over SoA arrays x[component][N] (same layout as the C-ABI).
+    `OracleChain(desc, fast="ref")` drives the reference's own code instead (oracle/ref_driver.cpp), same methods."""
 
     KIN_FIELDS = ("T_tool", "T_links", "jacobian", "twist", "dtwist", "dtwist_lin", "dtwist_nonlin", "ddtwist",
                   "ddtwist_lin", "ddtwist_nonlin", "torque")
 
-    def __init__(self, desc: ChainDesc, fast: bool = False):
+    def __init__(self, desc: ChainDesc, fast=False):
         self._l = lib(fast)
         cdesc, keep = to_ctypes(desc)
         self._h = self._l.lib.oracle_chain_create(ctypes.byref(cdesc))

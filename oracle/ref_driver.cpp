@@ -1,0 +1,337 @@
+// ref_driver.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Batch driver around the REFERENCE's own rosdyn::Chain (the headers under /root/reference/rosdyn_core/include are compiled where
+// they lie; see oracle/Makefile target _ref).  Eigen3 / urdfdom / roscpp are not installed in this image, so the third-party headers
+// the reference includes are the small stand-ins of oracle/shim/ (dense arithmetic restated as plain loops, urdf structs without the
+// XML parser, logging dropped).  Every kinematic / dynamic formula that runs here is the reference's source text:
+//   Joint::fromUrdf, Link::fromUrdf, Chain::init, setInputJointsName, computeFrames, computeScrews, getTransformations, getJacobian,
+//   getTwist, getDTwist*, getDDTwist*, getWrench, getJointTorque, getRegressor, getJointInertia, getNominalParameters
+//   (internal/primitives_impl.h) and spacevect_algebra.h.
+// The exported symbols mirror oracle/rosdyn_oracle.c one to one (same names, same SoA layouts), so oracle/oracle.py drives either
+// library; tests/test_reference_build.py checks the restatement against this build.  Only tests/ and bench.py's CPU legs load it.
+#include <rosdyn_core/primitives.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../include/rosdyn_b200.h" /* descriptor structs only */
+
+namespace
+{
+struct RefChain
+{
+  std::shared_ptr<urdf::Model> model;
+  rosdyn::ChainPtr chain;
+  std::vector<std::string> input_names;
+  std::vector<rosdyn::ChainPtr> per_thread;  // rosdyn::Chain is stateful and not reentrant: one clone() per worker (primitives.h:554)
+  int nJ = 0, nL = 0, n_in = 0;
+  // chains for `nthreads` workers (0 = all); worker 0 uses the original
+  int workers(int nthreads)
+  {
+    int nt = 1;
+#ifdef _OPENMP
+    nt = nthreads <= 0 ? omp_get_max_threads() : nthreads;
+#endif
+    (void)nthreads;
+    while ((int)per_thread.size() < nt)
+    {
+      if (per_thread.empty())
+        per_thread.push_back(chain);
+      else
+      {
+        rosdyn::ChainPtr c = chain->clone();
+        c->setInputJointsName(input_names);
+        per_thread.push_back(c);
+      }
+    }
+    return nt;
+  }
+};
+int tid()
+{
+#ifdef _OPENMP
+  return omp_get_thread_num();
+#else
+  return 0;
+#endif
+}
+
+// rotation matrix (row-major) -> unit quaternion, Shepperd's method; the reference turns it back into a matrix (urdf_parser.h:44-50)
+urdf::Rotation rot_to_quat(const double* R)
+{
+  urdf::Rotation q;
+  const double m00 = R[0], m01 = R[1], m02 = R[2], m10 = R[3], m11 = R[4], m12 = R[5], m20 = R[6], m21 = R[7], m22 = R[8];
+  const double tr = m00 + m11 + m22;
+  if (tr > 0)
+  {
+    const double s = std::sqrt(tr + 1.0) * 2;
+    q.w = 0.25 * s;
+    q.x = (m21 - m12) / s;
+    q.y = (m02 - m20) / s;
+    q.z = (m10 - m01) / s;
+  }
+  else if (m00 > m11 && m00 > m22)
+  {
+    const double s = std::sqrt(1.0 + m00 - m11 - m22) * 2;
+    q.w = (m21 - m12) / s;
+    q.x = 0.25 * s;
+    q.y = (m01 + m10) / s;
+    q.z = (m02 + m20) / s;
+  }
+  else if (m11 > m22)
+  {
+    const double s = std::sqrt(1.0 + m11 - m00 - m22) * 2;
+    q.w = (m02 - m20) / s;
+    q.x = (m01 + m10) / s;
+    q.y = 0.25 * s;
+    q.z = (m12 + m21) / s;
+  }
+  else
+  {
+    const double s = std::sqrt(1.0 + m22 - m00 - m11) * 2;
+    q.w = (m10 - m01) / s;
+    q.x = (m02 + m20) / s;
+    q.y = (m12 + m21) / s;
+    q.z = 0.25 * s;
+  }
+  const double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  q.x /= n;
+  q.y /= n;
+  q.z /= n;
+  q.w /= n;
+  return q;
+}
+
+Eigen::VectorXd gather(const double* x, int n_in, int64_t ld, int64_t i)
+{
+  Eigen::VectorXd v(n_in);
+  for (int j = 0; j < n_in; j++) v(j) = x ? x[(int64_t)j * ld + i] : 0.0;
+  return v;
+}
+
+void put_vec6(double* dst, int64_t ld, int64_t i, const rosdyn::VectorOfVector6d& v)
+{
+  if (!dst) return;
+  for (size_t l = 0; l < v.size(); l++)
+    for (int k = 0; k < 6; k++) dst[(int64_t)(6 * l + k) * ld + i] = v[l](k);
+}
+}  // namespace
+
+extern "C" {
+
+const char* oracle_kind(void) { return "reference"; }
+int oracle_max_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void* oracle_chain_create(const rdb_chain_desc* d)
+{
+  try
+  {
+    if (!d || d->n_joints < 0) return nullptr;
+    auto rc = std::make_unique<RefChain>();
+    rc->nJ = d->n_joints;
+    rc->nL = d->n_joints + 1;
+    rc->n_in = d->n_inputs;
+    rc->model = std::make_shared<urdf::Model>();
+    std::vector<std::shared_ptr<urdf::Link>> links(rc->nL);
+    for (int l = 0; l < rc->nL; l++)
+    {
+      links[l] = std::make_shared<urdf::Link>();
+      links[l]->name = "link_" + std::to_string(l);
+      const rdb_link_desc& L = d->links[l];
+      links[l]->inertial = std::make_shared<urdf::Inertial>();
+      urdf::Inertial& in = *links[l]->inertial;
+      in.mass = L.mass;
+      in.origin.position.x = L.cog[0];
+      in.origin.position.y = L.cog[1];
+      in.origin.position.z = L.cog[2];
+      in.origin.rotation = rot_to_quat(L.inertial_rot);
+      in.ixx = L.inertia[0];
+      in.ixy = L.inertia[1];
+      in.ixz = L.inertia[2];
+      in.iyy = L.inertia[3];
+      in.iyz = L.inertia[4];
+      in.izz = L.inertia[5];
+    }
+    std::vector<std::string> input_names(rc->n_in);
+    for (int k = 0; k < rc->n_in; k++) input_names[k] = "__unlisted_input_" + std::to_string(k);  // no such joint: column of S stays zero
+    for (int j = 0; j < rc->nJ; j++)
+    {
+      const rdb_joint_desc& J = d->joints[j];
+      auto uj = std::make_shared<urdf::Joint>();
+      uj->name = "joint_" + std::to_string(j);
+      uj->type = J.type == RDB_JOINT_REVOLUTE ? urdf::Joint::REVOLUTE : (J.type == RDB_JOINT_PRISMATIC ? urdf::Joint::PRISMATIC : urdf::Joint::FIXED);
+      uj->axis.x = J.axis[0];
+      uj->axis.y = J.axis[1];
+      uj->axis.z = J.axis[2];
+      uj->parent_to_joint_origin_transform.position.x = J.xyz[0];
+      uj->parent_to_joint_origin_transform.position.y = J.xyz[1];
+      uj->parent_to_joint_origin_transform.position.z = J.xyz[2];
+      uj->parent_to_joint_origin_transform.rotation = rot_to_quat(J.rot);
+      uj->limits = std::make_shared<urdf::JointLimits>();
+      uj->limits->lower = -1.0e9;
+      uj->limits->upper = 1.0e9;
+      uj->limits->velocity = 10.0;
+      uj->limits->effort = 100.0;
+      uj->parent_link_name = links[j]->name;
+      uj->child_link_name = links[j + 1]->name;
+      links[j]->child_joints.push_back(uj);
+      links[j]->child_links.push_back(links[j + 1]);
+      links[j + 1]->parent_joint = uj;
+      if (J.input_index >= 0 && J.input_index < rc->n_in) input_names[J.input_index] = uj->name;
+    }
+    rc->model->root_link_ = links[0];
+    Eigen::Vector3d g;
+    g << d->gravity[0], d->gravity[1], d->gravity[2];
+    rc->chain = rosdyn::createChain(*rc->model, links.front()->name, links.back()->name, g);
+    if (!rc->chain) return nullptr;
+    rc->chain->setInputJointsName(input_names);
+    rc->input_names = input_names;
+    return rc.release();
+  }
+  catch (const std::exception&)
+  {
+    return nullptr;
+  }
+}
+
+void oracle_chain_destroy(void* c) { delete static_cast<RefChain*>(c); }
+int oracle_chain_joints_number(const void* c) { return (int)static_cast<const RefChain*>(c)->chain->getJointsNumber(); }
+int oracle_chain_inputs_number(const void* c) { return (int)static_cast<const RefChain*>(c)->chain->getActiveJointsNumber(); }
+
+void oracle_nominal_parameters(const void* c, double* out)
+{
+  const Eigen::VectorXd p = static_cast<const RefChain*>(c)->chain->getNominalParameters();
+  for (Eigen::Index k = 0; k < p.size(); k++) out[k] = p(k);
+}
+
+void oracle_kinematics_batch(const void* cv, int64_t n, int64_t ld, const double* q, const double* dq, const double* ddq, const double* dddq,
+                             int64_t ld_out, double* T_tool, double* T_links, double* jacobian, double* twist, double* dtwist,
+                             double* dtwist_lin, double* dtwist_nonlin, double* ddtwist, double* ddtwist_lin, double* ddtwist_nonlin,
+                             double* torque, int nthreads)
+{
+  RefChain* rc = static_cast<RefChain*>(const_cast<void*>(cv));
+  const int nt = rc->workers(nthreads);
+  const int n_in = rc->n_in, nL = rc->nL;
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (int64_t i = 0; i < n; i++)
+  {
+    rosdyn::Chain& ch = *rc->per_thread[tid()];
+    const Eigen::VectorXd vq = gather(q, n_in, ld, i), vdq = gather(dq, n_in, ld, i), vddq = gather(ddq, n_in, ld, i),
+                          vdddq = gather(dddq, n_in, ld, i);
+    if (T_tool || T_links)
+    {
+      const rosdyn::VectorOfAffine3d& T = ch.getTransformations(vq);
+      for (int l = 0; l < nL; l++)
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 4; c++)
+          {
+            const double v = T[l].matrix()(r, c);
+            if (T_links) T_links[(int64_t)(12 * l + 4 * r + c) * ld_out + i] = v;
+            if (T_tool && l == nL - 1) T_tool[(int64_t)(4 * r + c) * ld_out + i] = v;
+          }
+    }
+    if (jacobian)
+    {
+      const Eigen::Matrix6Xd& J = ch.getJacobian(vq);
+      for (int c = 0; c < n_in; c++)
+        for (int r = 0; r < 6; r++) jacobian[(int64_t)(6 * c + r) * ld_out + i] = J(r, c);
+    }
+    // order matters: the full recursions first (their direct paths), the linear / non-linear parts afterwards, so that the
+    // reference's "sum of the cached parts" shortcuts (primitives_impl.h:1108-1112, 1205-1209) are not taken
+    if (twist) put_vec6(twist, ld_out, i, ch.getTwist(vq, vdq));
+    if (dtwist) put_vec6(dtwist, ld_out, i, ch.getDTwist(vq, vdq, vddq));
+    if (ddtwist) put_vec6(ddtwist, ld_out, i, ch.getDDTwist(vq, vdq, vddq, vdddq));
+    if (torque)
+    {
+      const Eigen::VectorXd& t = ch.getJointTorque(vq, vdq, vddq);
+      for (int k = 0; k < n_in; k++) torque[(int64_t)k * ld_out + i] = t(k);
+    }
+    if (dtwist_lin) put_vec6(dtwist_lin, ld_out, i, ch.getDTwistLinearPart(vq, vddq));
+    if (dtwist_nonlin) put_vec6(dtwist_nonlin, ld_out, i, ch.getDTwistNonLinearPart(vq, vdq));
+    if (ddtwist_lin) put_vec6(ddtwist_lin, ld_out, i, ch.getDDTwistLinearPart(vq, vdddq));
+    if (ddtwist_nonlin) put_vec6(ddtwist_nonlin, ld_out, i, ch.getDDTwistNonLinearPart(vq, vdq, vddq));
+  }
+}
+
+void oracle_regressor_torque_batch(const void* cv, int64_t n, int64_t ld, const double* q, const double* dq, const double* ddq, int64_t ld_out,
+                                   double* phi, double* torque, int nthreads)
+{
+  RefChain* rc = static_cast<RefChain*>(const_cast<void*>(cv));
+  const int nt = rc->workers(nthreads);
+  const int n_in = rc->n_in, P = 10 * rc->nJ;
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (int64_t i = 0; i < n; i++)
+  {
+    rosdyn::Chain& ch = *rc->per_thread[tid()];
+    const Eigen::VectorXd vq = gather(q, n_in, ld, i), vdq = gather(dq, n_in, ld, i), vddq = gather(ddq, n_in, ld, i);
+    const Eigen::VectorXd t = ch.getJointTorque(vq, vdq, vddq);
+    const Eigen::MatrixXd R = ch.getRegressor(vq, vdq, vddq);
+    if (phi)
+      for (int c = 0; c < P; c++)
+        for (int r = 0; r < n_in; r++) phi[(int64_t)(c * n_in + r) * ld_out + i] = R(r, c);
+    if (torque)
+      for (int k = 0; k < n_in; k++) torque[(int64_t)k * ld_out + i] = t(k);
+  }
+}
+
+void oracle_inertia_batch(const void* cv, int64_t n, int64_t ld, const double* q, int64_t ld_out, double* inertia, int nthreads)
+{
+  RefChain* rc = static_cast<RefChain*>(const_cast<void*>(cv));
+  const int nt = rc->workers(nthreads);
+  const int n_in = rc->n_in;
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (int64_t i = 0; i < n; i++)
+  {
+    rosdyn::Chain& ch = *rc->per_thread[tid()];
+    const Eigen::MatrixXd& M = ch.getJointInertia(gather(q, n_in, ld, i));
+    for (int c = 0; c < n_in; c++)
+      for (int r = 0; r < n_in; r++) inertia[(int64_t)(c * n_in + r) * ld_out + i] = M(r, c);
+  }
+}
+
+// normal equations of the reference's regressor / torque with long-double accumulation
+void oracle_regressor_gram(const void* cv, int64_t n, int64_t ld, const double* q, const double* dq, const double* ddq, const double* tau_meas,
+                           double* gram, double* rhs, double* tau_sq)
+{
+  const RefChain* rc = static_cast<const RefChain*>(cv);
+  rosdyn::Chain& ch = *rc->chain;
+  const int n_in = rc->n_in, P = 10 * rc->nJ;
+  std::vector<long double> G((size_t)P * P, 0.0L), b(P, 0.0L);
+  long double tt = 0.0L;
+  for (int64_t i = 0; i < n; i++)
+  {
+    const Eigen::VectorXd vq = gather(q, n_in, ld, i), vdq = gather(dq, n_in, ld, i), vddq = gather(ddq, n_in, ld, i);
+    Eigen::VectorXd t = ch.getJointTorque(vq, vdq, vddq);
+    if (tau_meas) t = gather(tau_meas, n_in, ld, i);
+    const Eigen::MatrixXd R = ch.getRegressor(vq, vdq, vddq);
+    for (int r = 0; r < n_in; r++)
+    {
+      tt += (long double)t(r) * t(r);
+      for (int c = 0; c < P; c++)
+      {
+        const long double x = R(r, c);
+        if (x == 0.0L) continue;
+        b[c] += x * t(r);
+        for (int c2 = 0; c2 < P; c2++) G[(size_t)c * P + c2] += x * R(r, c2);
+      }
+    }
+  }
+  for (int k = 0; k < P * P; k++) gram[k] = (double)G[k];
+  for (int k = 0; k < P; k++) rhs[k] = (double)b[k];
+  if (tau_sq) *tau_sq = (double)tt;
+}
+
+}  // extern "C"

@@ -6,12 +6,17 @@
  * "port" CPU baseline of bench.py.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may link or call it; the product (rosdyn_b200/) never does.
  *
- * PARITY UNPINNED by the reference's own tests: rosdyn_core/test/test.cpp holds no EXPECT/ASSERT, ships no
- * golden vectors and its URDF is external.  The reference cannot be
- * compiled in this image (needs Eigen3, urdfdom, roscpp, eigen_matrix_utils, kinematics_filters - none
- * present, no network).  What pins this file instead: (1) an independent numpy transcription of the same
- * reference lines (oracle/numpy_transcription.py) whose outputs are committed as tests/golden/ *.npz,
- * (2) the algebraic invariants of SURVEY.md section 4 and the UR10 zero-pose known answer.
+ * PINNING.  The reference's own tests hold nothing to pin against (rosdyn_core/test/test.cpp has no EXPECT/ASSERT, ships no golden
+ * vectors and its URDF is external), and Eigen3 / urdfdom / roscpp are not installed here.
+ * This file is therefore pinned against OUTPUTS OF THE REFERENCE ITSELF: oracle/_ref/librosdyn_ref.so is the reference's own
+ * rosdyn::Chain (primitives.h, internal/primitives_impl.h, spacevect_algebra.h, urdf_parser.h compiled where they lie under
+ * /root/reference by oracle/Makefile `ref`), with the absent third-party headers replaced by the stand-ins of oracle/shim/
+ * (mini_eigen.h: dense products as plain loops; urdf structs; ros logging dropped).  tests/test_reference_build.py compares every
+ * output of this file with that build live (<= 1e-12) and with its committed outputs tests/golden/ref_*.npz (generator
+ * tests/golden/make_golden_ref.py).  What that build does NOT pin is Eigen's own rounding order inside fixed-size products
+ * (Eigen3 is un-vendored and unpinned by the reference, CMakeLists.txt:31): a few ulp, far inside the 1e-10 acceptance bound.
+ * Also kept: (1) the independent numpy transcription oracle/numpy_transcription.py -> tests/golden/<chain>.npz, (2) the algebraic
+ * invariants of SURVEY.md section 4 and the UR10 zero-pose known answer.
  * Third-party arithmetic restated here: Eigen3 fixed-size products/cross/transposes (version unpinned by the
  * reference, CMakeLists.txt:31) and libm sin/cos.
  *

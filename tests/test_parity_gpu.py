@@ -43,10 +43,13 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
+@pytest.mark.parametrize("source", ["numpy_transcription", "reference"])
 @pytest.mark.parametrize("name", CHAINS)
-def test_golden_vectors(name, chains, golden, torch):
+def test_golden_vectors(name, source, chains, golden, torch):
+    """source = "reference": outputs of the reference's own rosdyn::Chain (tests/golden/ref_*.npz, made by
+    tests/golden/make_golden_ref.py from oracle/_ref); "numpy_transcription": the independent transcription (make_golden.py)."""
     d, ch, _ = chains(name)
-    g = golden(name)
+    g = golden(name if source == "numpy_transcription" else "ref_" + name)
     dev = [torch.tensor(g[k], device="cuda") for k in ("q", "dq", "ddq", "dddq")]
     K = ch.kinematics(*dev, want=KIN)
     for k in KIN:
