@@ -177,6 +177,46 @@ rdb_status rdb_inertia_batch(const rdb_chain* chain, const rdb_samples* in, doub
 rdb_status rdb_regressor_gram_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                     double* tau_sq, int32_t accumulate, void* stream);
 
+/* ---- additive joint components ------------------------------------------------------------
+ * The reference models joint friction / elasticity as per-joint "components" whose regressor columns are appended to the
+ * inertial regressor by the identification code (base_component.h:124-139).  Column blocks, in the order given here:
+ *   RDB_COMPONENT_FRICTION_POLY1 (FirstOrderPolynomialFriction, friction_polynomial1.h:45-52):   [sign, omega]
+ *        omega = clamp(Dq_j, -max_velocity, max_velocity), sign = clamp(omega / min_velocity, -1, 1)
+ *   RDB_COMPONENT_FRICTION_POLY2 (SecondOrderPolynomialFriction, friction_polynomial2.h:42-58):  [sign, omega, omega^2 sign]
+ *        sign = 0 (omega == 0), +-1 beyond +-min_velocity, omega / min_velocity in between
+ *   RDB_COMPONENT_IDEAL_SPRING   (IdealSpring, ideal_spring.h:64-70):                            [q_j, 1]
+ * Constructor rules are mirrored: min_velocity < 1e-6 becomes 1e-6; POLY1 max_velocity <= 0 becomes 1e6
+ * (friction_polynomial1.h:74-87); POLY2 with max_velocity < 0 sets min_velocity = 1e6 and keeps max_velocity, as the
+ * reference does (friction_polynomial2.h:91-96).  Every column is zero except in the row of its joint. */
+typedef enum rdb_component_type
+{
+  RDB_COMPONENT_FRICTION_POLY1 = 1,
+  RDB_COMPONENT_FRICTION_POLY2 = 2,
+  RDB_COMPONENT_IDEAL_SPRING = 3
+} rdb_component_type;
+#define RDB_MAX_COMPONENTS 64
+typedef struct rdb_component_desc
+{
+  int32_t type;        /* rdb_component_type                                                                */
+  int32_t input_index; /* the joint it acts on, as a position in q/Dq (ComponentBase::getJointNumber)       */
+  double min_velocity; /* friction constants "min_velocity" / "max_velocity"; ignored by the spring         */
+  double max_velocity;
+} rdb_component_desc;
+int32_t rdb_component_columns(int32_t type); /* 2, 3, 2; -1 for an unknown type (ComponentBase::getParametersNumber) */
+rdb_status rdb_chain_set_components(rdb_chain* chain, int32_t n, const rdb_component_desc* components); /* n = 0 clears */
+int32_t rdb_chain_component_columns(const rdb_chain* chain); /* total number of component columns Pc */
+/* ComponentBase::getRegressor of every component, side by side: phi_c[Pc * n_inputs][ld_out], plane col*n_inputs+row. */
+rdb_status rdb_components_regressor_batch(const rdb_chain* chain, const rdb_samples* in, double* phi_c, int64_t ld_out, void* stream);
+/* ComponentBase::getTorque summed over the components: torque[n_inputs][ld_out] (+)= phi_c(sample) * parameters;
+ * parameters[Pc] is a HOST array (the components' nominal parameters).  IdealSpring::getTorque indexes q out of range in
+ * the reference (ideal_spring.h:57); this entry uses regressor * parameters, the evident intent. */
+rdb_status rdb_components_torque_batch(const rdb_chain* chain, const rdb_samples* in, const double* parameters, double* torque,
+                                       int64_t ld_out, int32_t accumulate, void* stream);
+/* Normal equations of the extended model [Phi | Phi_c] with Pt = 10*n_joints + Pc columns: gram[Pt*Pt], rhs[Pt], tau_sq[1];
+ * same conventions as rdb_regressor_gram_batch.  tau_s = tau_meas when given, else the rigid-body getJointTorque. */
+rdb_status rdb_regressor_gram_ext_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+                                        double* tau_sq, int32_t accumulate, void* stream);
+
 /* ---- host-buffer convenience wrappers (pointers are HOST pointers; copies + sync inside) ---------- */
 rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out);
 rdb_status rdb_torque_batch_host(const rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out);

@@ -87,6 +87,27 @@ def lib(fast=False) -> _Lib:
     return _libs[fast]
 
 
+class CComponentDesc(ctypes.Structure):  # image of rdb_component_desc (include/rosdyn_b200.h)
+    _fields_ = [("type", ctypes.c_int32), ("input_index", ctypes.c_int32), ("min_velocity", ctypes.c_double), ("max_velocity", ctypes.c_double)]
+
+
+def components_regressor(components, n_in: int, q, dq, fast=False) -> np.ndarray:
+    """components: [(type 1|2|3, input_index, min_velocity, max_velocity), ...] -> phi_c[Pc*n_in][N] (plane col*n_in+row).
+    fast="ref" runs the reference's own component classes (friction_polynomial1.h, friction_polynomial2.h, ideal_spring.h)."""
+    L = lib(fast).lib
+    arr = (CComponentDesc * max(len(components), 1))()
+    for k, (t, j, lo, hi) in enumerate(components):
+        arr[k].type, arr[k].input_index, arr[k].min_velocity, arr[k].max_velocity = int(t), int(j), float(lo), float(hi)
+    Pc = sum(3 if int(c[0]) == 2 else 2 for c in components)
+    q, dq = _c(q, n_in), _c(dq, n_in)
+    n = q.shape[1]
+    out = np.full((Pc * n_in, n), np.nan)
+    L.oracle_components_regressor_batch.argtypes = [ctypes.c_int, ctypes.POINTER(CComponentDesc), ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                                    _dbl_p, _dbl_p, ctypes.c_int64, _dbl_p]
+    L.oracle_components_regressor_batch(len(components), arr, n_in, n, n, _ptr(q), _ptr(dq), n, _ptr(out))
+    return out
+
+
 def fill_uniform(n_planes: int, n: int, seed: int, stream_id: int) -> np.ndarray:
     x = np.empty((n_planes, n))
     lib().lib.oracle_fill_uniform(_ptr(x), n_planes, n, n, seed, stream_id)

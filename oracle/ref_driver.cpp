@@ -334,4 +334,54 @@ void oracle_regressor_gram(const void* cv, int64_t n, int64_t ld, const double* 
   if (tau_sq) *tau_sq = (double)tt;
 }
 
+// The reference's component classes themselves (friction_polynomial1.h, friction_polynomial2.h, ideal_spring.h), constructed through the
+// stand-in parameter store exactly as rosdyn_identification would configure them; nominal coefficients are arbitrary (the regressor
+// does not depend on them).
+void oracle_components_regressor_batch(int n_comp, const rdb_component_desc* comp, int n_in, int64_t n, int64_t ld, const double* q,
+                                       const double* dq, int64_t ld_out, double* phi_c)
+{
+  ros::NodeHandle nh;
+  const std::string robot = "checker_robot";
+  std::vector<std::string> names(n_in);
+  for (int k = 0; k < n_in; k++) names[k] = "in_" + std::to_string(k);
+  nh.setParam(robot + "/joint_names", names);
+  int col = 0;
+  for (int k = 0; k < n_comp; k++)
+  {
+    const rdb_component_desc& c = comp[k];
+    const std::string jn = names.at(c.input_index);
+    rosdyn::ComponentPtr cp;
+    if (c.type == RDB_COMPONENT_IDEAL_SPRING)
+    {
+      nh.setParam(robot + "/" + jn + "/spring/coefficients", std::map<std::string, double>{{"elasticity", 3.0}, {"offset_effort", 0.5}});
+      nh.setParam(robot + "/" + jn + "/spring/constants", std::map<std::string, double>{});
+      cp.reset(new rosdyn::IdealSpring(jn, robot, nh));
+    }
+    else
+    {
+      nh.setParam(robot + "/" + jn + "/friction/constants", std::map<std::string, double>{{"min_velocity", c.min_velocity}, {"max_velocity", c.max_velocity}});
+      if (c.type == RDB_COMPONENT_FRICTION_POLY1)
+      {
+        nh.setParam(robot + "/" + jn + "/friction/coefficients", std::map<std::string, double>{{"coloumb", 1.0}, {"viscous", 2.0}});
+        cp.reset(new rosdyn::FirstOrderPolynomialFriction(jn, robot, nh));
+      }
+      else
+      {
+        nh.setParam(robot + "/" + jn + "/friction/coefficients",
+                    std::map<std::string, double>{{"coloumb", 1.0}, {"first_order_viscous", 2.0}, {"second_order_viscous", 0.3}});
+        cp.reset(new rosdyn::SecondOrderPolynomialFriction(jn, robot, nh));
+      }
+    }
+    const int nc = (int)cp->getParametersNumber();
+    for (int64_t i = 0; i < n; i++)
+    {
+      Eigen::VectorXd vq = gather(q, n_in, ld, i), vdq = gather(dq, n_in, ld, i), vddq = Eigen::VectorXd::Zero(n_in);
+      const Eigen::MatrixXd R = cp->getRegressor(vq, vdq, vddq);
+      for (int p = 0; p < nc; p++)
+        for (int r = 0; r < n_in; r++) phi_c[((int64_t)(col + p) * n_in + r) * ld_out + i] = R(r, p);
+    }
+    col += nc;
+  }
+}
+
 }  // extern "C"

@@ -812,6 +812,63 @@ static uint64_t splitmix64(uint64_t x)
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
+/* ------------------------------------------------------------------ additive joint components
+ * FirstOrderPolynomialFriction::computeRegressor   friction_polynomial1.h:45-52 (+ ctor rules :74-87)
+ * SecondOrderPolynomialFriction::computeRegressor  friction_polynomial2.h:42-58 (+ ctor rules :84-96, threshold quirk included)
+ * IdealSpring::getRegressor                        ideal_spring.h:64-70
+ * phi_c planes col*n_in+row; a component's columns are zero except in the row of its joint (dense m_regressor). */
+static int or_comp_cols(int type) { return type == RDB_COMPONENT_FRICTION_POLY2 ? 3 : 2; }
+void oracle_components_regressor_batch(int n_comp, const rdb_component_desc* comp, int n_in, int64_t n, int64_t ld, const double* q,
+                                       const double* dq, int64_t ld_out, double* phi_c)
+{
+  int col = 0;
+  for (int k = 0; k < n_comp; k++)
+  {
+    const rdb_component_desc* c = &comp[k];
+    double thr = c->min_velocity, vmax = c->max_velocity;
+    if (c->type != RDB_COMPONENT_IDEAL_SPRING)
+    {
+      if (thr < 1e-6) thr = 1.0e-6;
+      if (c->type == RDB_COMPONENT_FRICTION_POLY1 && vmax <= 0) vmax = 1.0e6;
+      if (c->type == RDB_COMPONENT_FRICTION_POLY2 && vmax < 0) thr = 1.0e6;
+    }
+    const int nc = or_comp_cols(c->type);
+    for (int64_t i = 0; i < n; i++)
+    {
+      double v[3] = {0, 0, 0};
+      if (c->type == RDB_COMPONENT_IDEAL_SPRING)
+      {
+        v[0] = q ? q[(int64_t)c->input_index * ld + i] : 0.0;
+        v[1] = 1.0;
+      }
+      else
+      {
+        const double d = dq ? dq[(int64_t)c->input_index * ld + i] : 0.0;
+        const double omega = fmin(fmax(d, -vmax), vmax);
+        if (c->type == RDB_COMPONENT_FRICTION_POLY1)
+        {
+          v[0] = fmin(fmax(omega / thr, -1.0), 1.0);
+          v[1] = omega;
+        }
+        else
+        {
+          double sg;
+          if (omega == 0) sg = 0;
+          else if (omega > thr) sg = 1.0;
+          else if (omega < -thr) sg = -1.0;
+          else sg = omega / thr;
+          v[0] = sg;
+          v[1] = omega;
+          v[2] = pow(omega, 2.0) * sg;
+        }
+      }
+      for (int p = 0; p < nc; p++)
+        for (int r = 0; r < n_in; r++) phi_c[((int64_t)(col + p) * n_in + r) * ld_out + i] = (r == c->input_index) ? v[p] : 0.0;
+    }
+    col += nc;
+  }
+}
+
 void oracle_fill_uniform(double* x, int n_planes, int64_t n, int64_t ld, uint64_t seed, int stream_id)
 {
   for (int j = 0; j < n_planes; j++)

@@ -32,6 +32,10 @@ class CUrdfChain(ctypes.Structure):
                 ("ddq_max", ctypes.POINTER(ctypes.c_double)), ("tau_max", ctypes.POINTER(ctypes.c_double))]
 
 
+class CComponentDesc(ctypes.Structure):
+    _fields_ = [("type", i32), ("input_index", i32), ("min_velocity", ctypes.c_double), ("max_velocity", ctypes.c_double)]
+
+
 # every symbol include/rosdyn_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "rdb_abi_version": (i32, []),
@@ -55,6 +59,12 @@ SYMBOLS = {
     "rdb_regressor_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, i64, ctypes.c_void_p]),
     "rdb_inertia_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, ctypes.c_void_p]),
     "rdb_regressor_gram_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, _dp, _dp, i32, ctypes.c_void_p]),
+    "rdb_component_columns": (i32, [i32]),
+    "rdb_chain_set_components": (i32, [ctypes.c_void_p, i32, ctypes.POINTER(CComponentDesc)]),
+    "rdb_chain_component_columns": (i32, [ctypes.c_void_p]),
+    "rdb_components_regressor_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, ctypes.c_void_p]),
+    "rdb_components_torque_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(ctypes.c_double), _dp, i64, i32, ctypes.c_void_p]),
+    "rdb_regressor_gram_ext_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, _dp, _dp, i32, ctypes.c_void_p]),
     "rdb_kinematics_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(CKinematicsOut)]),
     "rdb_torque_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64]),
     "rdb_regressor_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, i64]),

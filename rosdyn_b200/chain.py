@@ -317,6 +317,82 @@ class Chain:
         return G, b, tt
 
 
+    # ------------------------------------------------------------------ additive joint components
+    def setComponents(self, components: Sequence[dict]) -> int:
+        """components: [{"type": "friction1" | "friction2" | "spring", "joint": <input joint name or index>,
+        "min_velocity": .., "max_velocity": ..}, ...] in column order (FirstOrderPolynomialFriction / SecondOrderPolynomialFriction /
+        IdealSpring, friction_polynomial1.h, friction_polynomial2.h, ideal_spring.h).  Returns the number of component columns."""
+        from ._lib import CComponentDesc
+        types = {"friction1": 1, "friction2": 2, "spring": 3}
+        names = self.getActiveJointsName()
+        arr = (CComponentDesc * max(len(components), 1))()
+        for k, c in enumerate(components):
+            j = c["joint"]
+            if isinstance(j, str):
+                if j not in names:
+                    # ComponentBase ctor: std::invalid_argument("Component Joint name ... is not a elemente of ...") (base_component.h:103)
+                    raise LookupError(f"Component Joint name '{j}' is not an input joint")
+                j = names.index(j)
+            arr[k].type = types[c["type"]] if isinstance(c["type"], str) else int(c["type"])
+            arr[k].input_index = int(j)
+            arr[k].min_velocity = float(c.get("min_velocity", 0.0))
+            arr[k].max_velocity = float(c.get("max_velocity", 0.0))
+        check(self._lib.rdb_chain_set_components(self._h, len(components), arr))
+        return self.getComponentColumns()
+
+    def getComponentColumns(self) -> int:
+        return int(self._lib.rdb_chain_component_columns(self._h))
+
+    def getComponentsRegressor(self, q, Dq):
+        """ComponentBase::getRegressor of every component side by side: n_act x Pc (x N); device arrays only."""
+        dev, single, n, arrs = self._prep([q, Dq, None, None])
+        if not dev:
+            raise ValueError("component entry points take device (torch CUDA) arrays")
+        Pc = self.getComponentColumns()
+        phi = self._alloc(dev, Pc * self.n_in, n, arrs[0])
+        s = self._samples(n, arrs)
+        check(self._lib.rdb_components_regressor_batch(self._h, ctypes.byref(s), _ptr(phi), max(n, 1), self._stream()))
+        r = _swap01(phi.reshape(Pc, self.n_in, n))
+        return r[..., 0] if single else r
+
+    def getComponentsTorque(self, q, Dq, parameters, out=None):
+        """Sum of ComponentBase::getTorque over the components (regressor * parameters); `out` accumulates onto an existing torque."""
+        dev, single, n, arrs = self._prep([q, Dq, None, None])
+        if not dev:
+            raise ValueError("component entry points take device (torch CUDA) arrays")
+        prm = np.ascontiguousarray(parameters, dtype=np.float64)
+        if prm.shape != (self.getComponentColumns(),):
+            raise ValueError("Input data dimensions mismatch")
+        tau = out if out is not None else self._alloc(dev, self.n_in, n, arrs[0])
+        s = self._samples(n, arrs)
+        check(self._lib.rdb_components_torque_batch(self._h, ctypes.byref(s), prm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _ptr(tau),
+                                                    _ld(tau), int(out is not None), self._stream()))
+        return tau[:, 0] if (single and out is None) else tau
+
+    def regressorGramExt(self, q, Dq, DDq, tau_meas=None, out=None):
+        """Normal equations of the extended model [Phi | Phi_components]: (G[Pt,Pt], b[Pt], tau_sq[1]), Pt = 10*nJ + Pc."""
+        dev, single, n, arrs = self._prep([q, Dq, DDq, None])
+        if not dev:
+            raise ValueError("component entry points take device (torch CUDA) arrays")
+        tau_arr = None
+        if tau_meas is not None:
+            _, _, nt, (tau_arr,) = self._prep([tau_meas])
+            if nt != n or _ld(tau_arr) != _ld(arrs[0]):
+                tau_arr = tau_arr.contiguous()
+                arrs = [None if a is None else a.contiguous() for a in arrs]
+        Pt = 10 * self.nJ + self.getComponentColumns()
+        acc = out is not None
+        if acc:
+            G, b, tt = out
+        else:
+            G = torch.empty((Pt, Pt), dtype=torch.float64, device=arrs[0].device)
+            b = torch.empty((Pt,), dtype=torch.float64, device=arrs[0].device)
+            tt = torch.empty((1,), dtype=torch.float64, device=arrs[0].device)
+        s = self._samples(n, arrs)
+        check(self._lib.rdb_regressor_gram_ext_batch(self._h, ctypes.byref(s), _ptr(tau_arr), _ptr(G), _ptr(b), _ptr(tt), int(acc), self._stream()))
+        return G, b, tt
+
+
 # ---------------------------------------------------------------------- helpers
 def _ptr(a):
     if a is None:

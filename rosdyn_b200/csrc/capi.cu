@@ -355,6 +355,86 @@ rdb_status rdb_regressor_gram_batch(const rdb_chain* chain, const rdb_samples* i
   return RDB_OK;
 }
 
+// ------------------------------------------------------------------------------------------- components (N2)
+int32_t rdb_component_columns(int32_t type)
+{
+  switch (type)
+  {
+    case RDB_COMPONENT_FRICTION_POLY1: return 2;
+    case RDB_COMPONENT_FRICTION_POLY2: return 3;
+    case RDB_COMPONENT_IDEAL_SPRING: return 2;
+  }
+  return -1;
+}
+
+rdb_status rdb_chain_set_components(rdb_chain* chain, int32_t n, const rdb_component_desc* components)
+{
+  if (!chain || n < 0 || n > RDB_MAX_COMPONENTS || (n > 0 && !components)) return fail(RDB_ERR_INVALID_ARG, "bad component list");
+  ComponentsDev C{};
+  for (int k = 0; k < n; k++)
+  {
+    const rdb_component_desc& d = components[k];
+    const int nc = rdb_component_columns(d.type);
+    if (nc < 0) return fail(RDB_ERR_INVALID_ARG, "unknown component type");
+    // "Component Joint name ... is not a elemente of joint_names" (base_component.h:103-104)
+    if (d.input_index < 0 || d.input_index >= chain->host.n_in) return fail(RDB_ERR_NOT_FOUND, "component joint is not an input joint");
+    ComponentDev& c = C.c[k];
+    c.type = d.type;
+    c.in = d.input_index;
+    c.col = C.cols;
+    c.ncols = nc;
+    c.thr = d.min_velocity;
+    c.vmax = d.max_velocity;
+    if (d.type != RDB_COMPONENT_IDEAL_SPRING)
+    {
+      if (c.thr < 1e-6) c.thr = 1.0e-6;                                             // friction_polynomial1.h:75-80, friction_polynomial2.h:84-89
+      if (d.type == RDB_COMPONENT_FRICTION_POLY1 && c.vmax <= 0) c.vmax = 1.0e6;    // friction_polynomial1.h:82-87
+      if (d.type == RDB_COMPONENT_FRICTION_POLY2 && c.vmax < 0) c.thr = 1.0e6;      // friction_polynomial2.h:91-96 (sic: the threshold)
+    }
+    C.cols += nc;
+  }
+  C.n = n;
+  chain->comps = C;
+  return RDB_OK;
+}
+
+int32_t rdb_chain_component_columns(const rdb_chain* chain) { return chain ? chain->comps.cols : -1; }
+
+rdb_status rdb_components_regressor_batch(const rdb_chain* chain, const rdb_samples* in, double* phi_c, int64_t ld_out, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  if (in->n == 0 || chain->comps.cols == 0) return RDB_OK;
+  if (!phi_c || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "phi_c: null or ld_out < n");
+  RDB_CUDA(launch_components_regressor(*chain, to_dev(in), phi_c, ld_out, (cudaStream_t)stream));
+  return RDB_OK;
+}
+
+rdb_status rdb_components_torque_batch(const rdb_chain* chain, const rdb_samples* in, const double* parameters, double* torque, int64_t ld_out,
+                                       int32_t accumulate, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  if (in->n == 0) return RDB_OK;
+  if (!torque || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "torque: null or ld_out < n");
+  if (chain->comps.cols > 0 && !parameters) return fail(RDB_ERR_INVALID_ARG, "parameters is null");
+  ComponentParams prm{};
+  for (int k = 0; k < chain->comps.cols; k++) prm.p[k] = parameters[k];
+  RDB_CUDA(launch_components_torque(*chain, to_dev(in), prm, torque, ld_out, accumulate, (cudaStream_t)stream));
+  return RDB_OK;
+}
+
+rdb_status rdb_regressor_gram_ext_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+                                        double* tau_sq, int32_t accumulate, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  if (in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (!gram || !rhs) return fail(RDB_ERR_INVALID_ARG, "gram / rhs must not be null");
+  RDB_CUDA(launch_gram(*const_cast<rdb_chain*>(chain), to_dev(in), tau_meas, gram, rhs, tau_sq, accumulate, (cudaStream_t)stream, true));
+  return RDB_OK;
+}
+
 rdb_status rdb_fill_uniform(double* x, int32_t n_planes, int64_t n, int64_t ld, uint64_t seed, int32_t stream_id, void* stream)
 {
   if (!x || n_planes < 0 || n_planes > 64 || n < 0 || ld < n || stream_id < 0 || stream_id > 3)

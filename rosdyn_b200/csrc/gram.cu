@@ -159,9 +159,10 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int npart
 }
 
 cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq, int accumulate,
-                        cudaStream_t st)
+                        cudaStream_t st, bool with_components)
 {
-  const int n_in = ch.host.n_in, P = 10 * ch.host.nj;
+  const int n_in = ch.host.n_in, Pr = 10 * ch.host.nj;     // rigid-body columns
+  const int P = Pr + (with_components ? ch.comps.cols : 0);  // + component columns (extended model)
   if (in.n <= 0 || n_in == 0 || P == 0)
   {
     if (!accumulate)
@@ -175,7 +176,7 @@ cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_m
   {
     // fused warp-specialised kernel (gram_fused.cu) whenever the chain fits it; RDB_GRAM_IMPL=v0 forces the general pipeline
     static const bool force_v0 = [] { const char* e = getenv("RDB_GRAM_IMPL"); return e && e[0] == 'v'; }();
-    if (!force_v0)
+    if (!force_v0 && P == Pr)
     {
       cudaError_t e = launch_gram_fused(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
       if (e != cudaErrorNotSupported) return e;
@@ -209,6 +210,11 @@ cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_m
     if (!ch.inputs_cover_all) cudaMemsetAsync(w_phi, 0, sizeof(double) * (size_t)chunk * (P * n_in + n_in), st);
     cudaError_t e = launch_dyn(ch, own_tau ? (DYN_REGRESSOR_ | DYN_TORQUE_) : DYN_REGRESSOR_, v, w_phi, own_tau ? w_tau : nullptr, nullptr, chunk, st);
     if (e != cudaSuccess) return e;
+    if (P > Pr)  // component planes follow the rigid-body planes (plane index = col * n_in + row)
+    {
+      e = launch_components_regressor(ch, v, w_phi + (size_t)Pr * n_in * chunk, chunk, st);
+      if (e != cudaSuccess) return e;
+    }
     const double* tau = own_tau ? w_tau : tau_meas + off;
     const int64_t tau_ld = own_tau ? chunk : in.ld;
     // the SYRK kernel takes one ld for both; when tau comes from the caller with another stride, stage it

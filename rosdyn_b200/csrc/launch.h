@@ -30,8 +30,25 @@ struct GramHostPipe
   int planes = -1;
 };
 
+// additive joint components (friction_polynomial1.h / friction_polynomial2.h / ideal_spring.h), device image
+struct ComponentDev
+{
+  int32_t type, in, col, ncols;
+  double thr, vmax;
+};
+struct ComponentsDev
+{
+  int32_t n, cols;
+  ComponentDev c[RDB_MAX_COMPONENTS];
+};
+struct ComponentParams
+{
+  double p[3 * RDB_MAX_COMPONENTS];
+};
+
 struct ChainHost
 {
+  ComponentsDev comps{};
   ChainDev<RDB_MAX_JOINTS> host;           // model constants, host copy
   ChainDev<RDB_MAX_JOINTS>* dev = nullptr;  // same, in device memory (generic kernels)
   int device = 0;
@@ -52,8 +69,13 @@ cudaError_t launch_fill_uniform(double* x, int n_planes, int64_t n, int64_t ld, 
 void fill_uniform_host(double* x, int n_planes, int64_t n, int64_t ld, uint64_t seed, int stream_id);
 
 // gram.cu
+// with_components: the extended model [Phi | Phi_c] (general pipeline); else the rigid-body columns only (fused kernel when it fits)
 cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
-                        int accumulate, cudaStream_t st);
+                        int accumulate, cudaStream_t st, bool with_components = false);
+// components.cu
+cudaError_t launch_components_regressor(const ChainHost& ch, const SamplesDev& in, double* phi_c, int64_t ld_out, cudaStream_t st);
+cudaError_t launch_components_torque(const ChainHost& ch, const SamplesDev& in, const ComponentParams& prm, double* torque, int64_t ld_out,
+                                     int accumulate, cudaStream_t st);
 cudaError_t fp64_peak(int kind, int reps, double* tflops);
 // gram_fused.cu: cudaErrorNotSupported when the chain does not fit the fused kernel
 cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
