@@ -217,6 +217,14 @@ rdb_status rdb_components_torque_batch(const rdb_chain* chain, const rdb_samples
 rdb_status rdb_regressor_gram_ext_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                         double* tau_sq, int32_t accumulate, void* stream);
 
+/* ---- normal-equation solve (HOST arrays, no reference code: the consumer is external) ------
+ * Minimum-norm least-squares solution of gram * parameters = rhs through a symmetric eigen-decomposition: the regressor is rank
+ * deficient in the standard parameters, so eigenvalues <= rel_tol * lambda_max (rel_tol <= 0: 1e-10) are discarded.
+ * gram[P*P] column-major (as rdb_regressor_gram_batch returns it, copied to the host), rhs[P]; outputs parameters[P],
+ * optional eigenvalues[P] (descending), rank, residual_sq = tau_sq - 2 pi^T rhs + pi^T gram pi = sum ||Phi pi - tau||^2. */
+rdb_status rdb_normal_equations_solve(int32_t P, const double* gram, const double* rhs, double tau_sq, double rel_tol, double* parameters,
+                                      double* eigenvalues, int32_t* rank, double* residual_sq);
+
 /* ---- host-buffer convenience wrappers (pointers are HOST pointers; copies + sync inside) ---------- */
 rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out);
 rdb_status rdb_torque_batch_host(const rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out);

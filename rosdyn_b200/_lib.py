@@ -65,6 +65,9 @@ SYMBOLS = {
     "rdb_components_regressor_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, ctypes.c_void_p]),
     "rdb_components_torque_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(ctypes.c_double), _dp, i64, i32, ctypes.c_void_p]),
     "rdb_regressor_gram_ext_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, _dp, _dp, i32, ctypes.c_void_p]),
+    "rdb_normal_equations_solve": (i32, [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.c_double,
+                                         ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32),
+                                         ctypes.POINTER(ctypes.c_double)]),
     "rdb_kinematics_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(CKinematicsOut)]),
     "rdb_torque_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64]),
     "rdb_regressor_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, i64]),

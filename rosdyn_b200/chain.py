@@ -434,6 +434,24 @@ def fill_uniform(n_planes: int, n: int, seed: int, stream_id: int, device=None):
     return x
 
 
+def solveNormalEquations(G, b, tau_sq=0.0, rel_tol: float = 1e-10):
+    """Minimum-norm least-squares solution of G pi = b (host, fp64).  G, b: numpy or torch (copied to the host).
+    Returns dict(parameters, eigenvalues, rank, residual_sq)."""
+    lib = _lib.load()
+    Gh = np.ascontiguousarray(G.detach().cpu().numpy() if _is_torch(G) else G, dtype=np.float64)
+    bh = np.ascontiguousarray(b.detach().cpu().numpy() if _is_torch(b) else b, dtype=np.float64)
+    tt = float(tau_sq.reshape(-1)[0]) if hasattr(tau_sq, "reshape") else float(tau_sq)
+    P = bh.shape[0]
+    if Gh.shape != (P, P):
+        raise ValueError("Input data dimensions mismatch")
+    prm, ev = np.zeros(P), np.zeros(P)
+    rank, res = ctypes.c_int32(0), ctypes.c_double(0.0)
+    dp = ctypes.POINTER(ctypes.c_double)
+    check(lib.rdb_normal_equations_solve(P, Gh.ctypes.data_as(dp), bh.ctypes.data_as(dp), tt, float(rel_tol), prm.ctypes.data_as(dp),
+                                         ev.ctypes.data_as(dp), ctypes.byref(rank), ctypes.byref(res)))
+    return {"parameters": prm, "eigenvalues": ev, "rank": int(rank.value), "residual_sq": float(res.value)}
+
+
 def fp64_peak(kind: str = "dmma", reps: int = 5) -> float:
     """Own FP64 roofline denominator in TFLOP/s: 'dfma' (vector pipe) or 'dmma' (mma.sync m8n8k4 f64)."""
     v = ctypes.c_double()

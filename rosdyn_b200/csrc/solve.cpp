@@ -1,0 +1,107 @@
+// solve.cpp -- the step right after the hot path in identification: solve the normal equations
+// G pi = b accumulated by rdb_regressor_gram_batch.  The reference holds no code for it (the consumer, rosdyn_identification, is an
+// external package: reference README.md:15).  Phi is rank deficient in the standard parameters (only the base parameters are
+// identifiable), so the solve is the minimum-norm least-squares solution through a symmetric eigen-decomposition of G
+// (cyclic Jacobi, fp64): pi = V_r diag(1/lambda_r) V_r^T b over the eigenvalues lambda > rel_tol * lambda_max.
+// Host code on purpose: G is (10 nJ + Pc)^2 <= a few hundred squared, microseconds of work next to billions of samples.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/rosdyn_b200.h"
+
+namespace rdb
+{
+rdb_status set_error(rdb_status s, const std::string& what);
+
+// eigen-decomposition of the symmetric n x n matrix a (column-major, destroyed): a = V diag(w) V^T, V column-major
+static void jacobi_eig(int n, std::vector<double>& a, std::vector<double>& V, std::vector<double>& w)
+{
+  V.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) V[(size_t)i * n + i] = 1.0;
+  auto A = [&](int i, int j) -> double& { return a[(size_t)j * n + i]; };
+  for (int sweep = 0; sweep < 100; sweep++)
+  {
+    double off = 0.0, diag = 0.0;
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n; i++) (i == j ? diag : off) += A(i, j) * A(i, j);
+    if (off <= 1e-32 * diag || off == 0.0) break;
+    for (int p = 0; p < n - 1; p++)
+      for (int q = p + 1; q < n; q++)
+      {
+        const double apq = A(p, q);
+        if (apq == 0.0) continue;
+        const double theta = (A(q, q) - A(p, p)) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < n; k++)
+        {
+          const double akp = A(k, p), akq = A(k, q);
+          A(k, p) = c * akp - s * akq;
+          A(k, q) = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++)
+        {
+          const double apk = A(p, k), aqk = A(q, k);
+          A(p, k) = c * apk - s * aqk;
+          A(q, k) = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++)
+        {
+          const double vkp = V[(size_t)p * n + k], vkq = V[(size_t)q * n + k];
+          V[(size_t)p * n + k] = c * vkp - s * vkq;
+          V[(size_t)q * n + k] = s * vkp + c * vkq;
+        }
+      }
+  }
+  w.resize(n);
+  for (int i = 0; i < n; i++) w[i] = A(i, i);
+}
+}  // namespace rdb
+
+extern "C" rdb_status rdb_normal_equations_solve(int32_t P, const double* gram, const double* rhs, double tau_sq, double rel_tol,
+                                                 double* parameters, double* eigenvalues, int32_t* rank, double* residual_sq)
+{
+  using namespace rdb;
+  if (P <= 0 || !gram || !rhs || !parameters) return set_error(RDB_ERR_INVALID_ARG, "normal_equations_solve: bad argument");
+  if (!(rel_tol > 0)) rel_tol = 1e-10;
+  std::vector<double> a((size_t)P * P), V, w;
+  for (int j = 0; j < P; j++)
+    for (int i = 0; i < P; i++) a[(size_t)j * P + i] = 0.5 * (gram[(size_t)j * P + i] + gram[(size_t)i * P + j]);
+  const std::vector<double> G(a);
+  jacobi_eig(P, a, V, w);
+  std::vector<int> order(P);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y]; });
+  const double wmax = std::max(w[order[0]], 0.0);
+  int r = 0;
+  std::fill(parameters, parameters + P, 0.0);
+  for (int k = 0; k < P; k++)
+  {
+    const int e = order[k];
+    if (eigenvalues) eigenvalues[k] = w[e];
+    if (!(w[e] > rel_tol * wmax) || wmax == 0.0) continue;
+    r++;
+    double vb = 0.0;
+    for (int i = 0; i < P; i++) vb += V[(size_t)e * P + i] * rhs[i];
+    const double coef = vb / w[e];
+    for (int i = 0; i < P; i++) parameters[i] += coef * V[(size_t)e * P + i];
+  }
+  if (rank) *rank = r;
+  if (residual_sq)
+  {
+    // || Phi pi - tau ||^2 = tau^T tau - 2 pi^T b + pi^T G pi
+    double pb = 0.0, pGp = 0.0;
+    for (int j = 0; j < P; j++)
+    {
+      pb += parameters[j] * rhs[j];
+      double s = 0.0;
+      for (int i = 0; i < P; i++) s += G[(size_t)j * P + i] * parameters[i];
+      pGp += parameters[j] * s;
+    }
+    *residual_sq = tau_sq - 2.0 * pb + pGp;
+  }
+  return RDB_OK;
+}
