@@ -177,6 +177,21 @@ rdb_status rdb_inertia_batch(const rdb_chain* chain, const rdb_samples* in, doub
 rdb_status rdb_regressor_gram_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                     double* tau_sq, int32_t accumulate, void* stream);
 
+/* Chain::getWrench / Chain::getJointTorque(q,Dq,DDq,ext_wrenches_in_link_frame) (PI.h:1225-1274).
+ * ext_wrenches[nL][6][ld_ext]: wrenches applied TO the links, in link frames, [force; torque] per link (NULL = none).  The reference
+ * brings them to the base frame with the TWIST transform spatialTranformation(-ext, T_bl) (PI.h:1255, SA.h:193-197); mirrored
+ * literally.  Outputs (each optional): torque[n_inputs][ld_out]; wrenches[nL][6][ld_out] = m_wrenches (base frame, at each link
+ * origin, link 0 included). */
+rdb_status rdb_wrench_batch(const rdb_chain* chain, const rdb_samples* in, const double* ext_wrenches, int64_t ld_ext, double* torque,
+                            double* wrenches, int64_t ld_out, void* stream);
+/* Chain::getJacobianLink(q, link) (PI.h:951-979): jacobian[n_inputs*6][ld_out], plane col*6+row, of link `link_index`
+ * (0 = base ... n_joints = tool), evaluated at q.  As in the reference the first K input joints get a column, K = number of
+ * input joints between the base and the link (the reference indexes m_active_joints by the loop counter, PI.h:970); with the
+ * default base->tool input order those are exactly the joints that move the link.  RDB_ERR_NOT_FOUND for a link outside the
+ * chain ("link ... is not member of the chain", PI.h:960). */
+rdb_status rdb_jacobian_link_batch(const rdb_chain* chain, const rdb_samples* in, int32_t link_index, double* jacobian, int64_t ld_out,
+                                   void* stream);
+
 /* ---- additive joint components ------------------------------------------------------------
  * The reference models joint friction / elasticity as per-joint "components" whose regressor columns are appended to the
  * inertial regressor by the identification code (base_component.h:124-139).  Column blocks, in the order given here:

@@ -176,6 +176,26 @@ class OracleChain:
         self._l.lib.oracle_inertia_batch(self._h, n, n, _ptr(q), n, _ptr(M), nthreads)
         return M
 
+    def wrench(self, q, dq, ddq, ext=None):
+        """getJointTorque(q,Dq,DDq,ext_wrenches_in_link_frame) and getWrench: (torque[n_in][N], wrenches[6 nL][N])."""
+        q, dq, ddq = (_c(x, self.n_in) for x in (q, dq, ddq))
+        ext = _c(ext, 6 * self.nL)
+        n = q.shape[1]
+        tau, w = np.zeros((self.n_in, n)), np.zeros((6 * self.nL, n))
+        f = self._l.lib.oracle_wrench_batch
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _dbl_p, _dbl_p, _dbl_p, _dbl_p, ctypes.c_int64, ctypes.c_int64, _dbl_p, _dbl_p]
+        f(self._h, n, n, _ptr(q), _ptr(dq), _ptr(ddq), _ptr(ext), n, n, _ptr(tau), _ptr(w))
+        return tau, w
+
+    def jacobian_link(self, q, link: int):
+        q = _c(q, self.n_in)
+        n = q.shape[1]
+        J = np.zeros((6 * self.n_in, n))
+        f = self._l.lib.oracle_jacobian_link_batch
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _dbl_p, ctypes.c_int, ctypes.c_int64, _dbl_p]
+        f(self._h, n, n, _ptr(q), int(link), n, _ptr(J))
+        return J
+
     def gram(self, q, dq, ddq, tau_meas=None):
         q, dq, ddq, tau_meas = (_c(x, self.n_in) for x in (q, dq, ddq, tau_meas))
         n = q.shape[1]

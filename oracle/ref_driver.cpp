@@ -302,6 +302,41 @@ void oracle_inertia_batch(const void* cv, int64_t n, int64_t ld, const double* q
   }
 }
 
+// Chain::getWrench + getJointTorque(q,Dq,DDq,ext) and Chain::getJacobianLink, through the reference's own methods
+void oracle_wrench_batch(const void* cv, int64_t n, int64_t ld, const double* q, const double* dq, const double* ddq, const double* ext,
+                         int64_t ld_ext, int64_t ld_out, double* torque, double* wrenches)
+{
+  const RefChain* rc = static_cast<const RefChain*>(cv);
+  rosdyn::Chain& ch = *rc->chain;
+  const int n_in = rc->n_in, nL = rc->nL;
+  for (int64_t i = 0; i < n; i++)
+  {
+    const Eigen::VectorXd vq = gather(q, n_in, ld, i), vdq = gather(dq, n_in, ld, i), vddq = gather(ddq, n_in, ld, i);
+    rosdyn::VectorOfVector6d e(nL);
+    for (int l = 0; l < nL; l++)
+      for (int k = 0; k < 6; k++) e[l](k) = ext ? ext[(int64_t)(6 * l + k) * ld_ext + i] : 0.0;
+    const Eigen::VectorXd t = ch.getJointTorque(vq, vdq, vddq, e);
+    if (torque)
+      for (int k = 0; k < n_in; k++) torque[(int64_t)k * ld_out + i] = t(k);
+    if (wrenches) put_vec6(wrenches, ld_out, i, ch.getWrench(vq, vdq, vddq, e));
+  }
+}
+void oracle_jacobian_link_batch(const void* cv, int64_t n, int64_t ld, const double* q, int link, int64_t ld_out, double* jac)
+{
+  const RefChain* rc = static_cast<const RefChain*>(cv);
+  rosdyn::Chain& ch = *rc->chain;
+  const int n_in = rc->n_in;
+  const std::string name = ch.getLinksName().at(link);
+  for (int64_t i = 0; i < n; i++)
+  {
+    const Eigen::VectorXd vq = gather(q, n_in, ld, i);
+    ch.getTransformation(vq);  // getJacobianLink itself ignores q (maybe_unused(q), primitives_impl.h:953): bring the frames up to date first
+    const Eigen::Matrix6Xd J = ch.getJacobianLink(vq, name);
+    for (int c = 0; c < n_in; c++)
+      for (int r = 0; r < 6; r++) jac[(int64_t)(6 * c + r) * ld_out + i] = c < J.cols() ? J(r, c) : 0.0;
+  }
+}
+
 // normal equations of the reference's regressor / torque with long-double accumulation
 void oracle_regressor_gram(const void* cv, int64_t n, int64_t ld, const double* q, const double* dq, const double* ddq, const double* tau_meas,
                            double* gram, double* rhs, double* tau_sq)

@@ -394,7 +394,10 @@ typedef struct oracle_out
   double* ddtwist;        /* [nL][6] */
   double* ddtwist_lin;    /* [nL][6] */
   double* ddtwist_nonlin; /* [nL][6] */
-  double* wrench;         /* [nL][6] getWrench with zero ext. wrenches */
+  double* wrench;         /* [nL][6] getWrench */
+  const double* ext;      /* [nL][6] ext_wrenches_in_link_frame (PI.h:1225), NULL = zero */
+  double* jac_link;       /* [n_in][6] getJacobianLink of link `link` (PI.h:951-979) */
+  int link;
   double* torque;         /* [n_in] */
   double* regressor;      /* [10 nJ][n_in] column-major n_in x 10nJ: phi[col*n_in+row] */
   double* inertia;        /* [n_in][n_in] column-major */
@@ -427,6 +430,24 @@ void oracle_eval(const oracle_chain* c, const double* q, const double* dq, const
       double d[3];
       dp(&st, nL - 1, nj + 1, d);
       spatial_translation(st.s[nj + 1], d, o->jacobian + 6 * idx);
+    }
+  }
+
+  /* getJacobianLink PI.h:966-976: joints = active joints between base and link; the loop indexes m_active_joints BY THE
+   * COUNTER (PI.h:970), i.e. the first joints.size() entries of the input-ordered active list */
+  if (o->jac_link)
+  {
+    int k_before = 0;
+    memset(o->jac_link, 0, sizeof(double) * 6 * n_in);
+    for (int nj = 0; nj < o->link && nj < nJ; nj++)
+      if (c->joint[nj].input_index >= 0) k_before++;
+    for (int nj = 0; nj < nJ; nj++)
+    {
+      int idx = c->joint[nj].input_index;
+      if (idx < 0 || idx >= k_before || c->joint[nj].type == RDB_JOINT_FIXED) continue;
+      double d[3];
+      dp(&st, o->link, nj + 1, d);
+      spatial_translation(st.s[nj + 1], d, o->jac_link + 6 * idx);
     }
   }
 
@@ -511,7 +532,9 @@ void oracle_eval(const oracle_chain* c, const double* q, const double* dq, const
         for (int i = 0; i < 3; i++) grav[3 + i] = -cr[i];
       }
       double zero6[6] = {-0.0, -0.0, -0.0, -0.0, -0.0, -0.0}; /* -ext with ext == 0 */
-      spatial_transformation(zero6, st.R[nl], st.p[nl], ext);
+      if (o->ext)
+        for (int i = 0; i < 6; i++) zero6[i] = -o->ext[6 * nl + i];
+      spatial_transformation(zero6, st.R[nl], st.p[nl], ext); /* PI.h:1255: the twist transform, applied to a wrench */
       if (nl < nL - 1)
       {
         double d[3], tr[6];
@@ -759,6 +782,47 @@ void oracle_inertia_batch(const oracle_chain* c, int64_t n, int64_t ld, const do
     o.inertia = bM;
     oracle_eval(c, vq, NULL, NULL, NULL, &o);
     for (int k = 0; k < n_in * n_in; k++) inertia[(int64_t)k * ld_out + i] = bM[k];
+  }
+}
+
+/* getWrench / getJointTorque with external wrenches (PI.h:1225-1274) and getJacobianLink (PI.h:951-979), batched */
+void oracle_wrench_batch(const oracle_chain* c, int64_t n, int64_t ld, const double* q, const double* dq, const double* ddq,
+                         const double* ext, int64_t ld_ext, int64_t ld_out, double* torque, double* wrenches)
+{
+  const int nL = c->nL, n_in = c->n_in;
+  for (int64_t i = 0; i < n; i++)
+  {
+    double vq[OR_MAXJ], vdq[OR_MAXJ], vddq[OR_MAXJ], bt[OR_MAXJ], bw[OR_MAXL * 6], be[OR_MAXL * 6];
+    gather_in(q, n_in, ld, i, vq);
+    gather_in(dq, n_in, ld, i, vdq);
+    gather_in(ddq, n_in, ld, i, vddq);
+    if (ext)
+      for (int k = 0; k < 6 * nL; k++) be[k] = ext[(int64_t)k * ld_ext + i];
+    oracle_out o;
+    memset(&o, 0, sizeof(o));
+    o.torque = bt;
+    o.wrench = bw;
+    o.ext = ext ? be : NULL;
+    oracle_eval(c, vq, vdq, vddq, NULL, &o);
+    if (torque)
+      for (int k = 0; k < n_in; k++) torque[(int64_t)k * ld_out + i] = bt[k];
+    if (wrenches)
+      for (int k = 0; k < 6 * nL; k++) wrenches[(int64_t)k * ld_out + i] = bw[k];
+  }
+}
+void oracle_jacobian_link_batch(const oracle_chain* c, int64_t n, int64_t ld, const double* q, int link, int64_t ld_out, double* jac)
+{
+  const int n_in = c->n_in;
+  for (int64_t i = 0; i < n; i++)
+  {
+    double vq[OR_MAXJ], bJ[OR_MAXJ * 6];
+    gather_in(q, n_in, ld, i, vq);
+    oracle_out o;
+    memset(&o, 0, sizeof(o));
+    o.jac_link = bJ;
+    o.link = link;
+    oracle_eval(c, vq, NULL, NULL, NULL, &o);
+    for (int k = 0; k < 6 * n_in; k++) jac[(int64_t)k * ld_out + i] = bJ[k];
   }
 }
 

@@ -249,6 +249,57 @@ class Chain:
             check(self._lib.rdb_torque_batch_host(self._h, ctypes.byref(s), _ptr(tau), max(n, 1)))
         return tau[:, 0] if single else tau
 
+    def getWrench(self, q, Dq, DDq, ext_wrenches_in_link_frame=None, with_torque: bool = False):
+        """Chain::getWrench (PI.h:1225-1262): nL x 6 (x N), base frame at each link origin; external wrenches nL x 6 (x N) are applied
+        TO the links in link frames.  with_torque also returns getJointTorque(q,Dq,DDq,ext) (PI.h:1264-1274).  Device arrays only."""
+        dev, single, n, arrs = self._prep([q, Dq, DDq, None])
+        if not dev:
+            raise ValueError("getWrench takes device (torch CUDA) arrays")
+        ext = None
+        if ext_wrenches_in_link_frame is not None:
+            ext = ext_wrenches_in_link_frame.to(torch.float64).reshape(6 * self.nL, -1).contiguous()
+            if ext.shape[1] != n:
+                raise ValueError("Input data dimensions mismatch")
+        w = self._alloc(dev, 6 * self.nL, n, arrs[0])
+        tau = self._alloc(dev, self.n_in, n, arrs[0]) if with_torque else None
+        s = self._samples(n, arrs)
+        check(self._lib.rdb_wrench_batch(self._h, ctypes.byref(s), _ptr(ext), max(n, 1), _ptr(tau), _ptr(w), max(n, 1), self._stream()))
+        w = w.reshape(self.nL, 6, n)
+        if single:
+            w = w[..., 0]
+            tau = tau[:, 0] if tau is not None else None
+        return (w, tau) if with_torque else w
+
+    def getJacobianLink(self, q, link_name):
+        """Chain::getJacobianLink(q, link_name) (PI.h:951-979): 6 x n_act (x N); std::invalid_argument for a link outside the chain."""
+        names = self.getLinksName()
+        if isinstance(link_name, str):
+            if link_name not in names:
+                raise ValueError(f"link {link_name} is not member of the chain")
+            link_name = names.index(link_name)
+        dev, single, n, arrs = self._prep([q, None, None, None])
+        if not dev:
+            raise ValueError("getJacobianLink takes device (torch CUDA) arrays")
+        J = self._alloc(dev, 6 * self.n_in, n, arrs[0])
+        s = self._samples(n, arrs)
+        check(self._lib.rdb_jacobian_link_batch(self._h, ctypes.byref(s), int(link_name), _ptr(J), max(n, 1), self._stream()))
+        r = _swap01(J.reshape(self.n_in, 6, n))
+        return r[..., 0] if single else r
+
+    def getTransformationLink(self, q, link_name):
+        """Chain::getTransformationLink (PI.h:912-925)."""
+        names = self.getLinksName()
+        if link_name not in names:
+            raise ValueError(f"link {link_name} is not member of the chain")
+        return self.getTransformations(q)[names.index(link_name)]
+
+    def getTwistLink(self, q, Dq, link_name):
+        """Chain::getTwistLink (PI.h:1016-1027)."""
+        names = self.getLinksName()
+        if link_name not in names:
+            raise ValueError(f"link {link_name} is not member of the chain")
+        return self.getTwist(q, Dq)[names.index(link_name)]
+
     def getJointTorqueNonLinearPart(self, q, Dq):
         """PI.h:1285-1293: getJointTorque with DDq = 0."""
         return self.getJointTorque(q, Dq, None)

@@ -355,6 +355,33 @@ rdb_status rdb_regressor_gram_batch(const rdb_chain* chain, const rdb_samples* i
   return RDB_OK;
 }
 
+rdb_status rdb_wrench_batch(const rdb_chain* chain, const rdb_samples* in, const double* ext_wrenches, int64_t ld_ext, double* torque,
+                            double* wrenches, int64_t ld_out, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  if (in->n == 0 || (!torque && !wrenches)) return RDB_OK;
+  if (ld_out < in->n || (ext_wrenches && ld_ext < in->n)) return fail(RDB_ERR_INVALID_ARG, "wrench_batch: ld < n");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((s = prezero(chain, torque, chain->host.n_in, ld_out, in->n, st)) != RDB_OK) return s;
+  RDB_CUDA(launch_aux(*chain, to_dev(in), ext_wrenches, ld_ext, torque, wrenches, nullptr, 0, ld_out, st));
+  return RDB_OK;
+}
+
+rdb_status rdb_jacobian_link_batch(const rdb_chain* chain, const rdb_samples* in, int32_t link_index, double* jacobian, int64_t ld_out,
+                                   void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  if (link_index < 0 || link_index > chain->host.nj) return fail(RDB_ERR_NOT_FOUND, "link is not member of the chain");
+  if (in->n == 0) return RDB_OK;
+  if (!jacobian || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "jacobian: null or ld_out < n");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((s = prezero(chain, jacobian, 6 * chain->host.n_in, ld_out, in->n, st)) != RDB_OK) return s;
+  RDB_CUDA(launch_aux(*chain, to_dev(in), nullptr, 0, nullptr, nullptr, jacobian, link_index, ld_out, st));
+  return RDB_OK;
+}
+
 // ------------------------------------------------------------------------------------------- components (N2)
 int32_t rdb_component_columns(int32_t type)
 {
