@@ -104,35 +104,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
 }
 
 // ---------------------------------------------------------------------------------------------- generator
-// sin and cos of NJ angles at once, branch free on the fast path (|q| <= 1e5: 3-term Cody-Waite reduction by pi/2 with exact FMA
-// products, then the fdlibm kernel polynomials on |r| <= pi/4; <= 1 ulp like the library), so that the whole walk of a sample is ONE
-// basic block and the scheduler can overlap the serial transform chain of link l+1 with the projections of link l.  Huge or
-// non-finite angles take the library sincos (Payne-Hanek) in a single, rarely executed branch.
-__device__ __forceinline__ void sincos_fast(double x, double& s, double& c)
-{
-  const double j = rint(x * 6.36619772367581382433e-01);
-  double r = fma(-j, 1.57079632679489655800e+00, x);
-  r = fma(-j, 6.12323399573676603587e-17, r);
-  r = fma(-j, -1.49738490485916983294e-33, r);  // pi/2 = hi + mid + lo (lo is negative)
-  const int q = (int)j;
-  const double z = r * r;
-  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(z, ps, 2.75573137070700676789e-06);
-  ps = fma(z, ps, -1.98412698298579493134e-04);
-  ps = fma(z, ps, 8.33333333332248946124e-03);
-  ps = fma(z, ps, -1.66666666666666324348e-01);
-  const double sr = fma(z * r, ps, r);
-  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(z, pc, -2.75573143513906633035e-07);
-  pc = fma(z, pc, 2.48015872894767294178e-05);
-  pc = fma(z, pc, -1.38888888888741095749e-03);
-  pc = fma(z, pc, 4.16666666666666019037e-02);
-  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-  const double ss = (q & 1) ? cr : sr, cc = (q & 1) ? sr : cr;
-  s = (q & 2) ? -ss : ss;
-  c = ((q + 1) & 2) ? -cc : cc;
-}
-
 template <int NJ>
 struct GenIn
 {
@@ -153,18 +124,7 @@ __device__ __forceinline__ void gen_load(const ChainDev<NJ>& C, const SamplesDev
 template <int NJ>
 __device__ __forceinline__ void gen_trig(GenIn<NJ>& x)
 {
-  bool big = false;
-#pragma unroll
-  for (int l = 0; l < NJ; l++)
-  {
-    sincos_fast(x.q[l], x.sv[l], x.cv[l]);
-    big |= !(fabs(x.q[l]) <= 1.0e5);
-  }
-  if (big)
-  {
-#pragma unroll
-    for (int l = 0; l < NJ; l++) sincos(x.q[l], &x.sv[l], &x.cv[l]);
-  }
+  trig_all<NJ>(x.q, x.sv, x.cv);
 }
 
 // One sample per lane: the rows [J0, J1) of getRegressor (+ getJointTorque) of sample i written to the slot.

@@ -30,7 +30,10 @@ namespace rdb
                         // 2.59 -> 3.20 G samples/s and the jerk walker 5.22 -> 5.51 vs. the uncapped 244-register build
 #endif
 #ifndef RDB_DYN_MINB
-#define RDB_DYN_MINB 4  // link-frame walker at <= 128 registers: materialised regressor 0.88 -> 0.91 (C6) / 0.92 -> 0.97 (C7) of HBM peak
+#define RDB_DYN_MINB 4  // link-frame walker, torque / inertia modes (FP64-pipe bound): <= 128 registers
+#endif
+#ifndef RDB_REG_MINB
+#define RDB_REG_MINB 3  // regressor modes (HBM-write bound): <= 168 registers, measured 0.92 -> 0.96 (C6) / 0.95 -> 0.99 (C7) of HBM peak vs. 4
 #endif
 
 template <int NJ_T>
@@ -76,14 +79,26 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
   V3 v = v3(0, 0, 0), w = v3(0, 0, 0), a = v3(0, 0, 0), al = v3(0, 0, 0);
   V3 g = v3(C.g);
 
+  // unrolled instantiations: every angle is loaded and its sin / cos evaluated up front (branch free), see trig_all
+  constexpr int NT = NJ_T > 0 ? NJ_T : 1;
+  double qv[NT], sv[NT], cv[NT];
+  if (NJ_T > 0)
+  {
+#pragma unroll
+    for (int l = 0; l < NT; l++) qv[l] = ld_in(in.q, C.joint[l].in, in.ld, i);
+    trig_all<NT>(qv, sv, cv);
+  }
+
 #pragma unroll
   for (int l = 0; l < (NJ_T > 0 ? NJ_T : nj); l++)
   {
     const JointDev& J = C.joint[l];
-    const double ql = ld_in(in.q, J.in, in.ld, i);
     double R[9];
     V3 t;
-    joint_transform(J, ql, R, t);
+    if (NJ_T > 0)
+      joint_transform_sc(J, qv[NJ_T > 0 ? l : 0], sv[NJ_T > 0 ? l : 0], cv[NJ_T > 0 ? l : 0], R, t);
+    else
+      joint_transform(J, ld_in(in.q, J.in, in.ld, i), R, t);
 
     // child-frame screw of joint l: [0;ax] revolute, [ax;0] prismatic, 0 fixed (R_pc^T axis_p == axis_j)
     const V3 axj = v3(J.ax);
@@ -261,7 +276,7 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
 }
 
 template <int NJ, int MODE>
-__global__ void __launch_bounds__(RDB_BLOCK, RDB_DYN_MINB) dyn_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, double* __restrict__ phi,
+__global__ void __launch_bounds__(RDB_BLOCK, (MODE & DYN_REGRESSOR) ? RDB_REG_MINB : RDB_DYN_MINB) dyn_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, double* __restrict__ phi,
                                                         double* __restrict__ tau, double* __restrict__ M, int64_t ld_out)
 {
   const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
@@ -335,8 +350,17 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // base <- current link
   V3 p = v3(0, 0, 0);
   Tw v = tw0(), a = tw0(), al = tw0(), an = tw0(), jf = tw0(), jl = tw0(), jn = tw0();
-  V3 sl[cJac ? CAP : 1], sa[cJac ? CAP : 1], pj[cJac ? CAP : 1];
+  // base-frame screw of joint j = [0; ab[j]] (revolute) / [ab[j]; 0] (prismatic) / 0 (fixed): one 3-vector + the joint type
+  V3 ab[cJac ? CAP : 1], pj[cJac ? CAP : 1];
   double tau[(MASK & K_TORQUE) ? CAP : 1];
+  constexpr int NT = NJ_T > 0 ? NJ_T : 1;
+  double qv[NT], sv[NT], cv[NT];
+  if (NJ_T > 0)
+  {
+#pragma unroll
+    for (int l = 0; l < NT; l++) qv[l] = ld_in(in.q, C.joint[l].in, in.ld, i);
+    trig_all<NT>(qv, sv, cv);
+  }
 
   // link 0 = base: identity pose, zero twists (primitives_impl.h:661-677, 697)
   if (wTl) st_pose(o.T_links, 0, ld, i, R, p);
@@ -352,10 +376,12 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
   for (int l = 0; l < (NJ_T > 0 ? NJ_T : nj); l++)
   {
     const JointDev& J = C.joint[l];
-    const double ql = ld_in(in.q, J.in, in.ld, i);
     double Rpc[9];
     V3 t;
-    joint_transform(J, ql, Rpc, t);
+    if (NJ_T > 0)
+      joint_transform_sc(J, qv[NJ_T > 0 ? l : 0], sv[NJ_T > 0 ? l : 0], cv[NJ_T > 0 ? l : 0], Rpc, t);
+    else
+      joint_transform(J, ld_in(in.q, J.in, in.ld, i), Rpc, t);
 
     // computeScrews (primitives_impl.h:879): screw of joint l in the base frame uses the PARENT link rotation
     const V3 axb = rot(R, v3(J.axp));
@@ -374,8 +400,7 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
 
     if (cJac)
     {
-      sl[l] = s.l;
-      sa[l] = s.a;
+      ab[l] = axb;
       pj[l] = p;
     }
 
@@ -452,8 +477,10 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
 #pragma unroll
       for (int j = 0; j <= l; j++)
       {
-        const V3 dj = pj[j] - p;
-        tau[j] += dot(sl[j], f) + dot(sa[j], cross_add(n, f, dj));
+        // s_j . dualTransl(w, p_j - p): the force part for a prismatic joint, the moment about the joint origin for a revolute one
+        const int tj = C.joint[j].type;
+        if (tj == RDB_JOINT_REVOLUTE) tau[j] += dot(ab[j], cross_add(n, f, pj[j] - p));
+        else if (tj == RDB_JOINT_PRISMATIC) tau[j] += dot(ab[j], f);
       }
     }
   }
@@ -469,9 +496,11 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
       const int r = C.joint[j].in;
       if (r >= 0)
       {
-        const V3 lin = cross_add(sl[j], sa[j], p - pj[j]);
+        const int tj = C.joint[j].type;
+        const V3 z = v3(0, 0, 0);
+        const V3 lin = tj == RDB_JOINT_REVOLUTE ? cross(ab[j], p - pj[j]) : (tj == RDB_JOINT_PRISMATIC ? ab[j] : z);
         st3(o.jacobian, (int64_t)6 * r, ld, i, lin);
-        st3(o.jacobian, (int64_t)6 * r + 3, ld, i, sa[j]);
+        st3(o.jacobian, (int64_t)6 * r + 3, ld, i, tj == RDB_JOINT_REVOLUTE ? ab[j] : z);
       }
     }
   }

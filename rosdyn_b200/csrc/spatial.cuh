@@ -50,6 +50,52 @@ __device__ __forceinline__ void mul33(const double* A, const double* B, double* 
     for (int j = 0; j < 3; j++) C[3 * i + j] = fma(A[3 * i], B[j], fma(A[3 * i + 1], B[3 + j], A[3 * i + 2] * B[6 + j]));
 }
 
+// sin and cos, branch free (|x| <= 1e5: 3-term Cody-Waite reduction by pi/2 with exact FMA products, then the fdlibm kernel polynomials on
+// |r| <= pi/4; <= 1 ulp like the library).  The walkers evaluate it for all joints of a sample up front, so that the whole walk is ONE
+// basic block and the scheduler can overlap the serial transform chain of link l+1 with the projections of link l.  Huge or non-finite
+// angles take the library sincos (Payne-Hanek) in a single, rarely executed branch (trig_all).
+__device__ __forceinline__ void sincos_fast(double x, double& s, double& c)
+{
+  const double j = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-j, 1.57079632679489655800e+00, x);
+  r = fma(-j, 6.12323399573676603587e-17, r);
+  r = fma(-j, -1.49738490485916983294e-33, r);  // pi/2 = hi + mid + lo (lo is negative)
+  const int q = (int)j;
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double sr = fma(z * r, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const double ss = (q & 1) ? cr : sr, cc = (q & 1) ? sr : cr;
+  s = (q & 2) ? -ss : ss;
+  c = ((q + 1) & 2) ? -cc : cc;
+}
+
+template <int N>
+__device__ __forceinline__ void trig_all(const double (&q)[N], double (&sv)[N], double (&cv)[N])
+{
+  bool big = false;
+#pragma unroll
+  for (int l = 0; l < N; l++)
+  {
+    sincos_fast(q[l], sv[l], cv[l]);
+    big |= !(fabs(q[l]) <= 1.0e5);
+  }
+  if (big)
+  {
+#pragma unroll
+    for (int l = 0; l < N; l++) sincos(q[l], &sv[l], &cv[l]);
+  }
+}
+
 // Joint::computedTpc (primitives_impl.h:38-47): parent<-child rotation R (row-major) and translation t (parent frame).
 __device__ __forceinline__ void joint_transform(const JointDev& J, double q, double* R, V3& t)
 {
@@ -58,6 +104,24 @@ __device__ __forceinline__ void joint_transform(const JointDev& J, double q, dou
   {
     double s, c;
     sincos(q, &s, &c);
+    const double c1 = 1.0 - c;
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = fma(c1, J.C[k], fma(s, J.B[k], J.A[k]));
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = J.A[k];
+    if (J.type == RDB_JOINT_PRISMATIC) t = axpy(t, v3(J.axp), q);
+  }
+}
+
+// same with sin q / cos q already known
+__device__ __forceinline__ void joint_transform_sc(const JointDev& J, double q, double s, double c, double* R, V3& t)
+{
+  t = v3(J.t);
+  if (J.type == RDB_JOINT_REVOLUTE)
+  {
     const double c1 = 1.0 - c;
 #pragma unroll
     for (int k = 0; k < 9; k++) R[k] = fma(c1, J.C[k], fma(s, J.B[k], J.A[k]));
