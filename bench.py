@@ -11,7 +11,10 @@ One step = one pass of the hot path over one batch of synthetic (q,Dq,DDq) sampl
 
 `value`  : device-resident inputs, CUDA-event timed, max over ranks.
 `e2e`    : the same metric through the C-ABI host-buffer entry point (pinned host inputs, H2D/D2H inside the timed region).
-`--impl reference` : the CPU restatement of the reference (oracle/, kind "port") on all host threads.
+`--impl reference` : the reference's CPU Chain loop on all host threads.  Two builds of it exist under oracle/: the plain-C restatement
+                     (kind "port") and oracle/_ref, the reference's own headers compiled against stand-in Eigen/urdf/ros headers (kind
+                     "reference"; its dense arithmetic is the stand-in's plain loops, so it is the slower of the two).  Both are timed; the
+                     line's value is the FASTER one (the conservative baseline), the other is reported beside it.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -101,6 +104,15 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic_per_sample(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per sample of the named kernel, from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None when there is no capture for it."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]["dram_bytes_per_sample"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -112,12 +124,13 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_run(chain_name: str, n: int, threads: int, reps: int = 1):
-    """getJointTorque + getRegressor per sample with the CPU restatement (oracle), all samples resident in host memory."""
+def cpu_run(chain_name: str, n: int, threads: int, reps: int = 1, kind="port"):
+    """getJointTorque + getRegressor per sample on the CPU, all samples resident in host memory.
+    kind "port": the plain-C restatement (oracle/rosdyn_oracle.c); "reference": the reference's own rosdyn::Chain (oracle/_ref)."""
     from oracle.oracle import OracleChain, fill_uniform
     from rosdyn_b200 import fixtures
     d = fixtures.by_name(chain_name)
-    oc = OracleChain(d)
+    oc = OracleChain(d, fast="ref" if kind == "reference" else False)
     q, dq, ddq = (fill_uniform(d.n_inputs, n, SEED, s) for s in range(3))
     best = None
     for _ in range(reps):
@@ -136,18 +149,38 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def reference_build_rate(chain_name: str, seconds: float, threads: int):
+    """The reference's own headers (oracle/_ref) on the same workload; None when that build is absent."""
+    try:
+        from oracle import oracle
+        if not oracle.have_ref():
+            return None
+        rate, _ = cpu_run(chain_name, 2000 * threads, threads, kind="reference")
+        n = int(max(2000 * threads, min(rate * seconds, 5_000_000)))
+        rate, dt = cpu_run(chain_name, n, threads, kind="reference")
+        return {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": f"{n} samples, rosdyn::Chain::getJointTorque + getRegressor of the reference's own headers compiled against the "
+                          f"stand-in Eigen of oracle/shim (one Chain::clone() per thread, OpenMP {threads} threads, {dt:.1f} s)"}
+    except Exception as e:  # the checker build must never take the bench down
+        return {"unavailable": repr(e)}
+
+
 def cpu_baseline(chain_name: str, seconds: float):
     threads = host_threads()
     rate, _ = cpu_run(chain_name, 20000 * max(1, threads // 4), threads)       # calibration
     n = int(max(50_000, min(rate * seconds, 50_000_000)))
     rate, dt = cpu_run(chain_name, n, threads)
-    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} samples of the same workload (getJointTorque + getRegressor per sample, oracle/rosdyn_oracle.c, "
-                      f"OpenMP {threads} threads, {dt:.1f} s)"}
+    out = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"{n} samples of the same workload (getJointTorque + getRegressor per sample, oracle/rosdyn_oracle.c, "
+                     f"OpenMP {threads} threads, {dt:.1f} s)"}
+    ref = reference_build_rate(chain_name, min(4.0, seconds), threads)
+    if ref is not None:
+        out["reference_build"] = ref   # slower than the port (plain-loop stand-in for Eigen): the port stays the baseline
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (restatement, kind 'port'; the Eigen/ROS original cannot be built here)."""
+    """--impl reference: the reference's CPU Chain loop on all host threads (the faster of the restatement and oracle/_ref)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -166,6 +199,10 @@ def run_reference(args):
         oc.regressor_torque(q, dq, ddq, nthreads=threads, store=False)
     dt = time.perf_counter() - t
     v = n * args.steps / dt
+    ref = reference_build_rate(args.chain, 4.0, threads)
+    kind, note = "port", "oracle/rosdyn_oracle.c (plain-C restatement of primitives_impl.h), OpenMP"
+    if ref and ref.get("value", 0.0) > v:   # report the faster CPU build: the conservative baseline
+        v, kind, note = ref["value"], "reference", ref["sample"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -173,8 +210,8 @@ def run_reference(args):
         "config": {"workload": f"{d.name}: getRegressor (6x70) + getJointTorque per sample (the GPU arm's workload), evaluated by the CPU "
                                f"restatement of the reference's Chain loop; bounded sample of {n} samples/step",
                    "chain": d.name, "samples_per_step": n, "mode": args.workload},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} samples/step x {args.steps} steps, oracle/rosdyn_oracle.c (plain-C restatement of primitives_impl.h), OpenMP"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{n} samples/step x {args.steps} steps, {note}", "reference_build": ref},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -311,14 +348,17 @@ def main():
             peaks64 = {"dmma_m8n8k4": fp64_peak("dmma", 3), "dfma": fp64_peak("dfma", 3), "dmma_and_dfma_interleaved": fp64_peak("mixed", 3)}
             peak = max(peaks64["dmma_m8n8k4"], peaks64["dfma"])
         ach = S * flop / (ms * 1e-3 / args.steps) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None, "traffic": None,
+        tps = ncu_traffic_per_sample(f"gram_fused_kernel<{d.n_joints}>:{args.chain}")
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None,
+                "traffic": (tps * S) if tps else None,
                 "peak_source": "own FP64 micro-benchmark on this GPU (max of DMMA m8n8k4 and DFMA); MEASURED_PEAKS.json has no FP64 figure",
                 "fp64_peaks_tflops": peaks64, "flop_per_sample": flop, "kernel": f"gram_fused_kernel<{d.n_joints}> (regressor generation + DMMA normal equations)"}
     else:
         bytes_per_sample = 8 * (3 * n_in + P * n_in + n_in)          # 3552 B for C6
         ach = S * bytes_per_sample / (ms * 1e-3 / args.steps) / 1e9
         peak = float(peaks["hbm_gbs"])
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        tps = ncu_traffic_per_sample(f"dyn_kernel<{d.n_joints},3>:{args.chain}")
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (tps * S) if tps else None,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})", "bytes_per_sample": bytes_per_sample, "kernel": f"dyn_kernel<{d.n_joints},3> (regressor+torque)"}
 
     if rank == 0:

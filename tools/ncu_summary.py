@@ -1,5 +1,9 @@
 """Summarise an .ncu-rep (read here, no GPU needed) into a small text file for profiles/.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/rNN_name.txt ["note"]"""
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/rNN_name.txt ["note"] [traffic-key samples-per-launch]
+With the last two arguments the DRAM traffic per sample of the first kernel in the report is merged into profiles/ncu_traffic.json
+under `traffic-key` (bench.py reads it for roofline.traffic)."""
+import json
+import os
 import csv
 import io
 import subprocess
@@ -32,6 +36,20 @@ def main():
         lines.append("")
     open(out, "w").write("\n".join(lines))
     print(out, len(lines), "lines")
+    if len(sys.argv) > 5:
+        key, nsamp = sys.argv[4], float(sys.argv[5])
+        r = rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(r[i].replace(",", "")) * scale[units[i]]
+        path = os.path.join(os.path.dirname(out) or ".", "ncu_traffic.json")
+        table = json.load(open(path)) if os.path.exists(path) else {}
+        table[key] = {"dram_bytes_per_sample": tot / nsamp, "samples_per_launch": nsamp, "report": os.path.basename(rep),
+                      "summary": os.path.basename(out), "kernel": r[hdr.index("Kernel Name")]}
+        json.dump(table, open(path, "w"), indent=1, sort_keys=True)
+        print(path, key, tot / nsamp, "B/sample")
 
 
 if __name__ == "__main__":
