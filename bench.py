@@ -216,6 +216,27 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the e2e leg are first-touched on the
+    GPU's NUMA node (8 ranks reading from one socket do not reach 8 x PCIe bandwidth).  Returns the previous affinity (restored before
+    the CPU baseline leg) or None when NVML / the syscall is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return old
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -234,6 +255,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    old_affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -361,6 +383,8 @@ def main():
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (tps * S) if tps else None,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})", "bytes_per_sample": bytes_per_sample, "kernel": f"dyn_kernel<{d.n_joints},3> (regressor+torque)"}
 
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.chain, args.cpu_seconds)
         out = {

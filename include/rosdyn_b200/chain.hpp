@@ -185,6 +185,51 @@ public:
   {
     check(rdb_regressor_gram_batch(m_h, &in, tau_meas, gram, rhs, tau_sq, accumulate ? 1 : 0, stream));
   }
+  // Chain::getWrench / getJointTorque(q,Dq,DDq,ext_wrenches_in_link_frame) (primitives_impl.h:1225-1274); ext [nL][6][ld_ext] or nullptr
+  void getWrench(const rdb_samples& in, const double* ext_wrenches, int64_t ld_ext, double* torque, double* wrenches, int64_t ld_out, void* stream = nullptr)
+  {
+    check(rdb_wrench_batch(m_h, &in, ext_wrenches, ld_ext, torque, wrenches, ld_out, stream));
+  }
+  // Chain::getJacobianLink (primitives_impl.h:951-979) by link index; std::invalid_argument for a link outside the chain (:960)
+  void getJacobianLink(const rdb_samples& in, int32_t link_index, double* jacobian, int64_t ld_out, void* stream = nullptr)
+  {
+    const rdb_status s = rdb_jacobian_link_batch(m_h, &in, link_index, jacobian, ld_out, stream);
+    if (s == RDB_ERR_NOT_FOUND) throw std::invalid_argument(rdb_last_error());
+    check(s);
+  }
+  // additive joint components (friction_polynomial1.h, friction_polynomial2.h, ideal_spring.h) as extra regressor columns
+  unsigned int setComponents(const std::vector<rdb_component_desc>& components)
+  {
+    const rdb_status s = rdb_chain_set_components(m_h, (int32_t)components.size(), components.data());
+    if (s == RDB_ERR_NOT_FOUND) throw std::invalid_argument(rdb_last_error());  // ComponentBase ctor, base_component.h:103-104
+    check(s);
+    return (unsigned int)rdb_chain_component_columns(m_h);
+  }
+  unsigned int getComponentColumns() const { return (unsigned int)rdb_chain_component_columns(m_h); }
+  void getComponentsRegressor(const rdb_samples& in, double* phi_c, int64_t ld_out, void* stream = nullptr)
+  {
+    check(rdb_components_regressor_batch(m_h, &in, phi_c, ld_out, stream));
+  }
+  void getComponentsTorque(const rdb_samples& in, const VectorXd& parameters, double* torque, int64_t ld_out, bool accumulate, void* stream = nullptr)
+  {
+    if (parameters.size() != getComponentColumns()) throw std::invalid_argument("Input data dimensions mismatch");
+    check(rdb_components_torque_batch(m_h, &in, parameters.data(), torque, ld_out, accumulate ? 1 : 0, stream));
+  }
+  void getRegressorGramExt(const rdb_samples& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq, bool accumulate, void* stream = nullptr)
+  {
+    check(rdb_regressor_gram_ext_batch(m_h, &in, tau_meas, gram, rhs, tau_sq, accumulate ? 1 : 0, stream));
+  }
+  // minimum-norm solution of the normal equations (host arrays); returns the rank
+  static int solveNormalEquations(const VectorXd& gram, const VectorXd& rhs, double tau_sq, VectorXd& parameters, double* residual_sq = nullptr,
+                                  double rel_tol = 1e-10)
+  {
+    const int32_t P = (int32_t)rhs.size();
+    if (gram.size() != (size_t)P * P) throw std::invalid_argument("Input data dimensions mismatch");
+    parameters.assign(P, 0.0);
+    int32_t rank = 0;
+    check(rdb_normal_equations_solve(P, gram.data(), rhs.data(), tau_sq, rel_tol, parameters.data(), nullptr, &rank, residual_sq));
+    return rank;
+  }
   // host pointers (copies and synchronisation inside)
   void computeTransformationsHost(const rdb_samples& in, const rdb_kinematics_out& out) { check(rdb_kinematics_batch_host(m_h, &in, &out)); }
   void getJointTorqueHost(const rdb_samples& in, double* torque, int64_t ld_out) { check(rdb_torque_batch_host(m_h, &in, torque, ld_out)); }

@@ -2,18 +2,25 @@
 //
 //   G (+)= sum_s Phi_s^T Phi_s ,  b (+)= sum_s Phi_s^T tau_s ,  tau_sq (+)= sum_s tau_s^T tau_s
 //
-// Phi never touches HBM.  Per CTA (1 per SM, 11 warps):
-//   * 3 generator warps: one thread walks the chain of one sample (same link-frame recursion as dyn_kernel,
-//     kernels.cu) and writes the augmented regressor rows [Phi_row | tau_row] of its 32 samples into one of
-//     three shared-memory slots (only the structurally non-zero columns, XOR-swizzled, conflict free);
-//   * 8 MMA warps: consume a slot as soon as it is full.  The contraction index k = (sample, joint row);
-//     a k-step is 4 samples of one joint row, so the zero pattern of Phi (row of chain joint j is zero left
-//     of column 10 j) is known at compile time and whole 8x8 tiles are skipped.  The upper-triangular tiles of the
-//     (P+1)x(P+1) augmented Gram matrix (45 for P = 70) stay in registers for the whole kernel: the two MMA warps of
-//     an SM sub-partition split them by tile-row parity (25 + 20 tiles), the four sub-partitions split the k-steps.
-//     tcgen05 has no f64 kind: the FP64 tensor path of sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA).
-//   * slots cycle through named barriers (full/empty), generation and DMMA overlap on the same FP64 pipes.
+// Phi never touches HBM.  Per CTA (1 per SM, 8 MMA warps + 3 generator warps):
+//   * generator warps: one thread walks the chain of one sample (same link-frame recursion as dyn_kernel, kernels.cu) and writes the
+//     augmented regressor rows [Phi_row | tau_row] of its 32 samples into one of three shared-memory slots (only the structurally
+//     non-zero columns, XOR-swizzled, conflict free).  The inputs of the next group are requested BEFORE waiting for the slot, so the
+//     DRAM latency hides behind the consumers; sin/cos of all joints are evaluated up front (branch free), so the walk is one basic block.
+//   * MMA warps: consume a slot as soon as it is full.  The contraction index k = (sample, joint row); a k-step is 4 samples of one
+//     joint row, so the zero pattern of Phi (row of chain joint j is zero left of column 10 j) is known at compile time and whole 8x8
+//     tiles are skipped.  The upper-triangular tiles of the (P+1)x(P+1) augmented Gram matrix (45 for P = 70) stay in registers for
+//     the whole kernel: the two MMA warps of an SM sub-partition split them by tile-row parity (25 + 20 tiles), the four
+//     sub-partitions split the k-steps.  tcgen05 has no f64 kind: the FP64 tensor path of sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA).
+//   * slots cycle through shared-memory mbarriers (full / empty per slot).
 // Per-CTA partials are summed in a fixed order by gram_fused_reduce_kernel (bit-reproducible for a given n).
+//
+// What bounds it (ncu, profiles/r01_gram_fused_v2_ncu.txt): DMMA and DFMA share ONE FP64 datapath; a DMMA occupies it for 16 cycles,
+// a DFMA for 2, and the warp scheduler grants it per instruction, so while the MMA warps work on a slot the generators crawl
+// (38 % of their time is math-pipe throttle) and the two phases effectively alternate.  The generator alone is latency bound (one warp
+// per 32 samples; the 227 KB of shared memory hold 96 samples in flight, which is what limits the generator warps to 3).  Splitting the
+// rows of a slot over more generator warps (GF_RSPLIT > 1) was measured SLOWER: each group is its own unrolled code and the kernel then
+// overflows the instruction cache (sm__icc hit rate 86 % -> 53 %).  Per-row slot release and an uneven k-split were also measured slower.
 #include <cuda_runtime.h>
 
 #include <algorithm>
