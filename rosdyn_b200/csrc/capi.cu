@@ -124,6 +124,7 @@ static rdb_status upload_model(ChainHost* ch)
   if (!ch->dev) RDB_CUDA(cudaMalloc(&ch->dev, sizeof(ch->host)));
   RDB_CUDA(cudaMemcpy(ch->dev, &ch->host, sizeof(ch->host), cudaMemcpyHostToDevice));
   cudaDeviceGetAttribute(&ch->sm_count, cudaDevAttrMultiProcessorCount, ch->device);
+  ch->model_version++;
   return RDB_OK;
 }
 
@@ -232,6 +233,7 @@ void rdb_chain_destroy(rdb_chain* chain)
   if (chain->dev) cudaFree(chain->dev);
   if (chain->gram.partials) cudaFree(chain->gram.partials);
   if (chain->gram.fused_partials) cudaFree(chain->gram.fused_partials);
+  if (chain->gram.fold_dev) cudaFree(chain->gram.fold_dev);
   GramHostPipe& hp = chain->gram_host;
   for (int k = 0; k < GramHostPipe::NSLOT; k++)
   {

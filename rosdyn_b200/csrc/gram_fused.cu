@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "launch.h"
 #include "spatial.cuh"
@@ -38,7 +39,8 @@ namespace rdb
 constexpr int GF_KSPLIT = 4;                       // MMA warps that share the k-steps of a slot (one per SM sub-partition)
 constexpr int GF_TS = GF_TSPLIT;                   // 1: each MMA warp owns all tiles; 2: two warps per sub-partition split the tile rows by parity
 constexpr int GF_MMA_WARPS = GF_KSPLIT * GF_TS;
-constexpr int GF_SLOTS = 3;      // 32-sample slots in shared memory (the 227 KB limit is what bounds the samples in flight)
+constexpr int GF_MAX_SLOTS = 4;  // 32-sample slots in shared memory: as many as fit the 227 KB (3 for a 7-joint chain, 4 from 6 joints down);
+                                 // 8 MMA + 4 generator warps = 3 warps per SM sub-partition is also what the 168-register budget allows
 #ifndef GF_RSPLIT
 #define GF_RSPLIT 1
 #endif
@@ -264,7 +266,7 @@ struct GramGeom
   static constexpr int T = (P + 1 + 7) / 8;       // tile columns of the augmented matrix
   static constexpr int NT = T * (T + 1) / 2;      // upper-triangular tiles
   static constexpr int NG = gf_groups(NJ);        // row groups = generator warps per slot
-  static constexpr int THREADS = 32 * (GF_MMA_WARPS + GF_SLOTS * NG);
+  __host__ __device__ static constexpr int threads(int slots) { return 32 * (GF_MMA_WARPS + slots * NG); }
   __host__ __device__ static constexpr int tile(int I, int J) { return I * T - I * (I - 1) / 2 + (J - I); }
   // tile rows owned by an MMA warp: all (TS == 1) or the rows of parity `par` (TS == 2)
   __host__ __device__ static constexpr bool owns(int I, int ts, int par) { return ts == 1 || (I & 1) == par; }
@@ -328,10 +330,10 @@ __device__ __forceinline__ void gram_consume(const GramRows& rows, const double*
 
 struct GramBars
 {
-  uint64_t full[GF_SLOTS][GF_MAXG], empty[GF_SLOTS][GF_MAXG];
+  uint64_t full[GF_MAX_SLOTS][GF_MAXG], empty[GF_MAX_SLOTS][GF_MAXG];
 };
 
-template <int NJ, int PAR, int GRP>
+template <int NJ, int SLOTS, int PAR, int GRP>
 __device__ __forceinline__ void gram_consume_groups(const GramRows& rows, const double* slot, GramBars* bars, int s, uint32_t parity, bool again,
                                                     int ks, int lane, int dbg, double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
 {
@@ -342,7 +344,7 @@ __device__ __forceinline__ void gram_consume_groups(const GramRows& rows, const 
     // k-steps (4 samples each) of this warp in this slot.  The generator warps sit on SM sub-partitions 0..2 and share the FP64 datapath
     // with the MMA warps there, sub-partition 3 has MMA warps only: it takes 3 of the 8 k-steps, the others 2, 2 and 1 (rotating with the slot)
     int k0, k1;
-    if (GF_UNEVEN && GF_SLOTS == 3 && GF_KSPLIT == 4)
+    if (GF_UNEVEN && SLOTS == 3 && GF_KSPLIT == 4)
     {
       const int o = ks == 3 ? 3 : (ks - s + 3) % 3;
       k0 = o == 3 ? 0 : (o == 0 ? 3 : (o == 1 ? 5 : 7));
@@ -359,11 +361,11 @@ __device__ __forceinline__ void gram_consume_groups(const GramRows& rows, const 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->empty[s][GRP]);
     }
-    gram_consume_groups<NJ, PAR, GRP + 1>(rows, slot, bars, s, parity, again, ks, lane, dbg, acc);
+    gram_consume_groups<NJ, SLOTS, PAR, GRP + 1>(rows, slot, bars, s, parity, again, ks, lane, dbg, acc);
   }
 }
 
-template <int NJ, int PAR>
+template <int NJ, int SLOTS, int PAR>
 __device__ __forceinline__ void gram_mma_role(const GramRows& rows, const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane, int dbg)
 {
   using G = GramGeom<NJ>;
@@ -372,15 +374,15 @@ __device__ __forceinline__ void gram_mma_role(const GramRows& rows, const Sample
 #pragma unroll
   for (int k = 0; k < NTP; k++) acc[k][0] = acc[k][1] = 0.0;
   const int64_t ngroups = (in.n + 31) / 32;
-  const int64_t stride = (int64_t)gridDim.x * GF_SLOTS;
+  const int64_t stride = (int64_t)gridDim.x * SLOTS;
   uint32_t parity = 0;
-  for (int64_t base = (int64_t)blockIdx.x * GF_SLOTS; base < ngroups; base += stride, parity ^= 1)
+  for (int64_t base = (int64_t)blockIdx.x * SLOTS; base < ngroups; base += stride, parity ^= 1)
   {
 #pragma unroll 1
-    for (int s = 0; s < GF_SLOTS; s++)
+    for (int s = 0; s < SLOTS; s++)
     {
       if (base + s >= ngroups) break;
-      gram_consume_groups<NJ, PAR, 0>(rows, smem + (size_t)s * rows.slot_doubles, bars, s, parity, base + s + stride < ngroups, ks, lane, dbg, acc);
+      gram_consume_groups<NJ, SLOTS, PAR, 0>(rows, smem + (size_t)s * rows.slot_doubles, bars, s, parity, base + s + stride < ngroups, ks, lane, dbg, acc);
     }
   }
   // fixed-order reduction over the k-split warps that own the same tiles, into shared memory (the slots are dead by now)
@@ -416,7 +418,7 @@ __device__ __forceinline__ void gram_mma_role(const GramRows& rows, const Sample
   }
 }
 
-template <int NJ, int GRP>
+template <int NJ, int SLOTS, int GRP>
 __device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const GramRows& rows, const SamplesDev& in, const double* __restrict__ tau_meas,
                                               double* smem, GramBars* bars, int gen_id, int lane, int dbg)
 {
@@ -428,10 +430,10 @@ __device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const GramR
       const int s = gen_id / G::NG;
       double* slot = smem + (size_t)s * rows.slot_doubles;
       const int64_t ngroups = (in.n + 31) / 32;
-      const int64_t stride = (int64_t)gridDim.x * GF_SLOTS;
+      const int64_t stride = (int64_t)gridDim.x * SLOTS;
       constexpr int J0 = gf_bound(NJ, G::NG, GRP), J1 = gf_bound(NJ, G::NG, GRP + 1);
       uint32_t parity = 1;  // first wait on an un-arrived barrier with parity 1 returns at once ("previous phase complete")
-      for (int64_t grp = (int64_t)blockIdx.x * GF_SLOTS + s; grp < ngroups; grp += stride, parity ^= 1)
+      for (int64_t grp = (int64_t)blockIdx.x * SLOTS + s; grp < ngroups; grp += stride, parity ^= 1)
       {
         // the inputs are requested BEFORE waiting for the slot: the DRAM latency hides behind the consumers' work on the previous group
         const int64_t i = grp * 32 + lane;
@@ -449,12 +451,12 @@ __device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const GramR
       }
     }
     else
-      gram_gen_role<NJ, GRP + 1>(C, rows, in, tau_meas, smem, bars, gen_id, lane, dbg);
+      gram_gen_role<NJ, SLOTS, GRP + 1>(C, rows, in, tau_meas, smem, bars, gen_id, lane, dbg);
   }
 }
 
-template <int NJ>
-__global__ void __launch_bounds__(GramGeom<NJ>::THREADS, 1)
+template <int NJ, int SLOTS>
+__global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
     gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const __grid_constant__ GramRows rows, const SamplesDev in,
                       const double* __restrict__ tau_meas, double* __restrict__ partial, const int dbg)
 {
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(GramGeom<NJ>::THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0)
   {
-    for (int s = 0; s < GF_SLOTS; s++)
+    for (int s = 0; s < SLOTS; s++)
       for (int g = 0; g < GF_MAXG; g++)
       {
         mbar_init(&bars.full[s][g], 1);             // lane 0 of the generator warp, after __syncwarp
@@ -473,17 +475,17 @@ __global__ void __launch_bounds__(GramGeom<NJ>::THREADS, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // group of (iteration it, CTA, slot s): (it*gridDim.x + blockIdx.x)*GF_SLOTS + s ; generator warp (s, g) writes the rows of group g
+  // group of (iteration it, CTA, slot s): (it*gridDim.x + blockIdx.x)*SLOTS + s ; generator warp (s, g) writes the rows of group g
   if (warp >= GF_MMA_WARPS)
   {
-    gram_gen_role<NJ, 0>(C, rows, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
+    gram_gen_role<NJ, SLOTS, 0>(C, rows, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
     return;
   }
   // ------------------------------------------------ MMA warps: k-split index = warp % 4 (its SM sub-partition), tile-row parity = warp / 4
   const int mma_id = warp;
   const int ks = mma_id % GF_KSPLIT;
-  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, 0>(rows, in, smem, &bars, ks, lane, dbg);
-  else gram_mma_role<NJ, 1>(rows, in, smem, &bars, ks, lane, dbg);
+  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, SLOTS, 0>(rows, in, smem, &bars, ks, lane, dbg);
+  else gram_mma_role<NJ, SLOTS, 1>(rows, in, smem, &bars, ks, lane, dbg);
   double* out = partial + (size_t)blockIdx.x * G::NT * 64;
   for (int k = mma_id * 32 + lane; k < G::NT * 64; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
 }
@@ -519,6 +521,162 @@ __global__ void gram_fused_reduce_kernel(const double* __restrict__ partial, int
     *tau_sq = accumulate ? *tau_sq + s : s;
 }
 
+// ---------------------------------------------------------------------------------------------- folded chain (host)
+// A joint that never moves (FIXED, or a joint that is not an input: the reference gives it q = 0) rigidly attaches its child link to the last
+// moving link A before it.  tau is linear in the inertial parameters, so the regressor block of such a link B is the block of A times a
+// CONSTANT 10x10 matrix:  Phi[:, B] = Phi[:, A] T_AB,  T_AB = d(parameters of the body referred to frame A) / d(parameters referred to
+// frame B)  (rotation + parallel-axis shift, linear in m, m c, I).  The fused kernel therefore runs on the chain with those joints folded
+// into the constant transform of the next moving joint (nJ' = moving joints, lumped parameters for tau), and the normal equations of the
+// reference's full parameter vector follow as  G = E^T G' E,  b = E^T b'  with E = blockdiag-like(I | T_AB) -- exact identities, evaluated
+// once per call on 70x70 numbers.  UR10-like C6 (6 revolute + fixed tool): 60 instead of 70 columns, 109 instead of 146 DMMA per 4 samples,
+// 21 instead of 28 (joint, link) pairs per sample, and a slot small enough for FOUR slots / generator warps per SM.
+struct FoldXf
+{
+  double R[9], t[3];  // x_parent = R x_child + t
+};
+static void xf_mul(const FoldXf& a, const double* Rb, const double* tb, FoldXf& c)
+{
+  for (int i = 0; i < 3; i++)
+  {
+    for (int j = 0; j < 3; j++) c.R[3 * i + j] = a.R[3 * i] * Rb[j] + a.R[3 * i + 1] * Rb[3 + j] + a.R[3 * i + 2] * Rb[6 + j];
+    c.t[i] = a.R[3 * i] * tb[0] + a.R[3 * i + 1] * tb[1] + a.R[3 * i + 2] * tb[2] + a.t[i];
+  }
+}
+static void rot9(const double* R, const double* M, double* out)  // R M
+{
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) out[3 * i + j] = R[3 * i] * M[j] + R[3 * i + 1] * M[3 + j] + R[3 * i + 2] * M[6 + j];
+}
+// T[c * 10 + p]: parameters [m, m c, Ixx, Ixy, Ixz, Iyy, Iyz, Izz] (inertia about the frame origin, frame axes; primitives_impl.h:399-417)
+// of a body referred to frame A as a linear function of the same referred to frame B, x_A = R x_B + t
+static void fold_param_map(const FoldXf& X, double* T)
+{
+  const double* R = X.R;
+  const double* t = X.t;
+  for (int p = 0; p < 10; p++)
+  {
+    double e[10] = {0};
+    e[p] = 1.0;
+    const double m = e[0], h[3] = {e[1], e[2], e[3]};
+    const double I[9] = {e[4], e[5], e[6], e[5], e[7], e[8], e[6], e[8], e[9]};
+    double Rh[3], RI[9], Io[9];
+    for (int i = 0; i < 3; i++) Rh[i] = R[3 * i] * h[0] + R[3 * i + 1] * h[1] + R[3 * i + 2] * h[2];
+    rot9(R, I, RI);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Io[3 * i + j] = RI[3 * i] * R[3 * j] + RI[3 * i + 1] * R[3 * j + 1] + RI[3 * i + 2] * R[3 * j + 2];  // R I R^T
+    const double rht = Rh[0] * t[0] + Rh[1] * t[1] + Rh[2] * t[2], tt = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        Io[3 * i + j] += (i == j ? 2.0 * rht + m * tt : 0.0) - (Rh[i] * t[j] + t[i] * Rh[j]) - m * t[i] * t[j];
+    const double o[10] = {m, Rh[0] + m * t[0], Rh[1] + m * t[1], Rh[2] + m * t[2], Io[0], Io[1], Io[2], Io[4], Io[5], Io[8]};
+    for (int c = 0; c < 10; c++) T[c * 10 + p] = o[c];
+  }
+}
+
+// (re)builds ch.gram.fold* for the current model; false when the folded chain is empty
+static cudaError_t fold_chain(ChainHost& ch)
+{
+  GramWorkspace& w = ch.gram;
+  if (w.fold_version == ch.model_version) return cudaSuccess;
+  const ChainDev<RDB_MAX_JOINTS>& H = ch.host;
+  ChainDev<RDB_MAX_JOINTS>& F = w.fold;
+  F = ChainDev<RDB_MAX_JOINTS>{};
+  F.n_in = H.n_in;
+  for (int k = 0; k < 3; k++) F.g[k] = H.g[k];
+  std::vector<double> T((size_t)H.nj * 100, 0.0);
+  std::vector<int32_t> kof(H.nj, -1);
+  FoldXf X{{1, 0, 0, 0, 1, 0, 0, 0, 1}, {0, 0, 0}};
+  int K = 0;
+  for (int l = 0; l < H.nj; l++)
+  {
+    const JointDev& J = H.joint[l];
+    if (J.in < 0)  // never moves: q = 0, T_pc = [A | t]
+    {
+      FoldXf Y;
+      xf_mul(X, J.A, J.t, Y);
+      X = Y;
+      if (K > 0)
+      {
+        kof[l] = K - 1;
+        fold_param_map(X, &T[(size_t)l * 100]);
+        for (int c = 0; c < 10; c++)
+          for (int p = 0; p < 10; p++) F.link[K - 1].pi[c] += T[(size_t)l * 100 + c * 10 + p] * H.link[l].pi[p];
+      }
+      continue;
+    }
+    JointDev& o = F.joint[K];
+    o = J;
+    rot9(X.R, J.A, o.A);
+    rot9(X.R, J.B, o.B);
+    rot9(X.R, J.C, o.C);
+    for (int i = 0; i < 3; i++)
+    {
+      o.t[i] = X.R[3 * i] * J.t[0] + X.R[3 * i + 1] * J.t[1] + X.R[3 * i + 2] * J.t[2] + X.t[i];
+      o.axp[i] = X.R[3 * i] * J.axp[0] + X.R[3 * i + 1] * J.axp[1] + X.R[3 * i + 2] * J.axp[2];
+    }
+    F.link[K] = H.link[l];
+    kof[l] = K;
+    for (int c = 0; c < 10; c++) T[(size_t)l * 100 + c * 10 + c] = 1.0;
+    K++;
+    X = FoldXf{{1, 0, 0, 0, 1, 0, 0, 0, 1}, {0, 0, 0}};
+  }
+  F.nj = K;
+  w.fold_identity = (K == H.nj);
+  if (!w.fold_identity && K > 0)
+  {
+    const size_t need = sizeof(double) * ((size_t)H.nj * 100 + (size_t)(10 * K + 1) * (10 * K + 1)) + sizeof(int32_t) * H.nj;
+    if (w.fold_bytes < need)
+    {
+      if (w.fold_dev) cudaFree(w.fold_dev);
+      w.fold_dev = nullptr;
+      w.fold_bytes = 0;
+      cudaError_t e = cudaMalloc(&w.fold_dev, need);
+      if (e != cudaSuccess) return e;
+      w.fold_bytes = need;
+    }
+    // layout: T (nj x 100) | reduced normal equations G' (P' x P'), b' (P'), tau_sq | link -> reduced link (nj ints)
+    cudaError_t e = cudaMemcpy(w.fold_dev, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(w.fold_dev + (size_t)H.nj * 100 + (size_t)(10 * K + 1) * (10 * K + 1), kof.data(), sizeof(int32_t) * H.nj, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+  }
+  w.fold_version = ch.model_version;
+  return cudaSuccess;
+}
+
+// G = E^T G' E, b = E^T b' (upper triangle computed, mirrored): one thread per entry of the full matrix, 100 products each
+__global__ void gram_fold_expand_kernel(const double* __restrict__ T, const int32_t* __restrict__ kof, const double* __restrict__ Gr,
+                                        const double* __restrict__ br, const double* __restrict__ tsr, int nj, int Pr, double* __restrict__ gram,
+                                        double* __restrict__ rhs, double* __restrict__ tau_sq, int accumulate)
+{
+  const int P = 10 * nj;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * (P + 1)) return;
+  const int a = e / (P + 1), b = e % (P + 1);  // b == P: right-hand side
+  if (e == P && tau_sq) *tau_sq = accumulate ? *tau_sq + *tsr : *tsr;
+  if (b < a) return;
+  const int la = a / 10, pa = a % 10, ka = kof[la];
+  double s = 0.0;
+  if (b == P)
+  {
+    if (ka >= 0)
+      for (int c = 0; c < 10; c++) s = fma(T[(size_t)la * 100 + c * 10 + pa], br[10 * ka + c], s);
+    rhs[a] = accumulate ? rhs[a] + s : s;
+    return;
+  }
+  const int lb = b / 10, pb = b % 10, kb = kof[lb];
+  if (ka >= 0 && kb >= 0)
+    for (int c = 0; c < 10; c++)
+    {
+      double r = 0.0;
+      for (int d = 0; d < 10; d++) r = fma(Gr[(size_t)(10 * kb + d) * Pr + 10 * ka + c], T[(size_t)lb * 100 + d * 10 + pb], r);
+      s = fma(T[(size_t)la * 100 + c * 10 + pa], r, s);
+    }
+  const double v = accumulate ? gram[(size_t)b * P + a] + s : s;
+  gram[(size_t)b * P + a] = v;
+  if (a != b) gram[(size_t)a * P + b] = v;
+}
+
 template <int NJ>
 static ChainDev<NJ> narrow_g(const ChainDev<RDB_MAX_JOINTS>& h)
 {
@@ -534,19 +692,19 @@ static ChainDev<NJ> narrow_g(const ChainDev<RDB_MAX_JOINTS>& h)
   return c;
 }
 
-template <int NJ>
+template <int NJ, int SLOTS>
 static cudaError_t launch_fused_nj(ChainHost& ch, const GramRows& rows, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs,
                                    double* tau_sq, int accumulate, cudaStream_t st)
 {
   using G = GramGeom<NJ>;
-  const size_t smem = sizeof(double) * (size_t)std::max(rows.slot_doubles * GF_SLOTS, G::NT * 64);
+  const size_t smem = sizeof(double) * (size_t)std::max(rows.slot_doubles * SLOTS, G::NT * 64);
   {
-    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   static const int dbg = [] { const char* e = getenv("RDB_GRAM_DEBUG"); return e ? atoi(e) : 0; }();  // 1: skip generation, 2: skip MMA (timing experiments only)
   const int64_t ngroups = (in.n + 31) / 32;
-  const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + GF_SLOTS - 1) / GF_SLOTS);
+  const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + SLOTS - 1) / SLOTS);
   const size_t need = sizeof(double) * (size_t)ch.sm_count * G::NT * 64;
   if (ch.gram.fused_bytes < need)
   {
@@ -557,37 +715,71 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const GramRows& rows, const Sa
     if (e != cudaSuccess) return e;
     ch.gram.fused_bytes = need;
   }
-  gram_fused_kernel<NJ><<<grid, G::THREADS, smem, st>>>(narrow_g<NJ>(ch.host), rows, in, tau_meas, ch.gram.fused_partials, dbg);
+  gram_fused_kernel<NJ, SLOTS><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), rows, in, tau_meas, ch.gram.fused_partials, dbg);
   count_launch();
-  gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, gram, rhs, tau_sq, accumulate);
+  if (ch.gram.fold_identity)
+  {
+    gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, gram, rhs, tau_sq, accumulate);
+    count_launch();
+    return cudaGetLastError();
+  }
+  // folded chain: reduce into G', b', then expand to the reference's full parameter vector
+  const int nj = ch.host.nj, Pr = G::P;
+  double* Tm = ch.gram.fold_dev;
+  double* Gr = Tm + (size_t)nj * 100;
+  double* br = Gr + (size_t)Pr * Pr;
+  double* tsr = br + Pr;
+  const int32_t* kof = reinterpret_cast<const int32_t*>(Gr + (size_t)(Pr + 1) * (Pr + 1));
+  gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, Gr, br, tsr, 0);
+  count_launch();
+  const int P = 10 * nj;
+  gram_fold_expand_kernel<<<(P * (P + 1) + 127) / 128, 128, 0, st>>>(Tm, kof, Gr, br, tsr, nj, Pr, gram, rhs, tau_sq, accumulate);
   count_launch();
   return cudaGetLastError();
 }
 
-// returns cudaErrorNotSupported when the chain does not fit the fused kernel (caller falls back to the v0 pipeline)
+// returns cudaErrorNotSupported when the chain does not fit the fused kernel (caller falls back to the general pipeline)
 cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
                               int accumulate, cudaStream_t st)
 {
-  const int nj = ch.host.nj;
-  if (nj < 1 || nj > 7 || in.n <= 0) return cudaErrorNotSupported;
+  if (in.n <= 0) return cudaErrorNotSupported;
+  static const bool no_fold = [] { const char* e = getenv("RDB_GRAM_NOFOLD"); return e && e[0] == '1'; }();  // timing experiments only
+  if (no_fold)
+  {
+    ch.gram.fold = ch.host;
+    ch.gram.fold_identity = true;
+    ch.gram.fold_version = ~0ull;
+  }
+  else
+  {
+    cudaError_t e = fold_chain(ch);
+    if (e != cudaSuccess) return e;
+  }
+  const ChainDev<RDB_MAX_JOINTS>& F = ch.gram.fold;
+  const int nj = F.nj;
+  if (nj < 1 || nj > 7) return cudaErrorNotSupported;
   GramRows rows;
   int off = 0;
   const int P = 10 * nj;
   for (int j = 0; j < 8; j++)
   {
     rows.base[j] = -1;
-    if (j < nj && ch.host.joint[j].in >= 0)
+    if (j < nj && F.joint[j].in >= 0)
     {
       rows.base[j] = off;
       off += (P + 1 - 10 * j) * 32;
     }
   }
   rows.slot_doubles = off;
-  if (off == 0 || sizeof(double) * (size_t)off * GF_SLOTS + 1024 > 227 * 1024) return cudaErrorNotSupported;
+  const size_t budget = 227 * 1024 - 1024;
+  if (off == 0 || sizeof(double) * (size_t)off * 3 > budget) return cudaErrorNotSupported;
+  const bool four = sizeof(double) * (size_t)off * 4 <= budget;
   switch (nj)
   {
-#define X(N) \
-  case N: return launch_fused_nj<N>(ch, rows, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
+#define X(N)                                                                                                    \
+  case N:                                                                                                       \
+    return four ? launch_fused_nj<N, 4>(ch, rows, in, tau_meas, gram, rhs, tau_sq, accumulate, st)             \
+                : launch_fused_nj<N, 3>(ch, rows, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
     X(1) X(2) X(3) X(4) X(5) X(6) X(7)
 #undef X
   }

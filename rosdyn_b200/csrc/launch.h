@@ -16,6 +16,12 @@ struct GramWorkspace
   int ctas = 0;
   double* fused_partials = nullptr;  // gram_fused.cu: per-CTA partial (P+1)x(P+1) upper-triangular tiles
   size_t fused_bytes = 0;
+  // gram_fused.cu: the chain with its never-moving joints folded away (fold_chain), rebuilt when the model changes
+  ChainDev<RDB_MAX_JOINTS> fold;
+  uint64_t fold_version = ~0ull;
+  bool fold_identity = true;   // nothing was folded: no expansion step
+  double* fold_dev = nullptr;  // parameter maps T | reduced normal equations | link -> reduced link
+  size_t fold_bytes = 0;
 };
 
 // persistent pipeline of rdb_regressor_gram_batch_host (capi.cu)
@@ -57,6 +63,7 @@ struct ChainHost
   GramWorkspace gram;
   GramHostPipe gram_host;
   int sm_count = 148;
+  uint64_t model_version = 0;  // bumped by every upload of the model (creation, rdb_chain_set_input_joints)
 };
 
 extern std::atomic<uint64_t> g_launches;

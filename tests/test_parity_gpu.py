@@ -120,6 +120,50 @@ def test_gram_against_long_double_oracle(name, chains, torch):
     assert np.max(np.abs(_np(b1) - 1.5 * br)) <= 1e-10 * np.max(np.abs(br)) * 1.5
 
 
+def _fold_case(case):
+    """Chains whose never-moving joints exercise every branch of the folded-chain Gram path (gram_fused.cu: fold_chain)."""
+    from rosdyn_b200.descriptor import FIXED
+    if case == "leading+double_interior":  # fixed joint at the base, two consecutive fixed joints inside, massive links everywhere
+        d = fixtures.random_chain(909, 9, p_prismatic=0.3, p_fixed=0.0)
+        for j in (0, 3, 4):
+            d.joints[j].type = FIXED
+        d.set_default_inputs()
+    elif case == "trailing_massive":  # C6 with a tool that has mass, cog and a full rotated inertia
+        d = fixtures.by_name("c6_perturbed")
+    elif case == "unlisted_and_permuted":  # moving-type joints that are not inputs behave as fixed at q = 0 (PI.h:865)
+        d = fixtures.by_name("c7_perturbed")
+        names = [j.name for j in d.joints]
+        d.set_input_joints([names[5], names[0], names[3], names[2]])
+    else:  # 11 joints, 7 of them moving: only the folded chain fits the fused kernel
+        d = fixtures.random_chain(777, 11, p_prismatic=0.2, p_fixed=0.0)
+        for j in (1, 4, 7, 10):
+            d.joints[j].type = FIXED
+        d.set_default_inputs()
+    return d
+
+
+@pytest.mark.parametrize("case", ["leading+double_interior", "trailing_massive", "unlisted_and_permuted", "long_chain"])
+def test_gram_folded_chain(case, torch):
+    from oracle.oracle import OracleChain
+    from rosdyn_b200.chain import Chain
+    d = _fold_case(case)
+    ch, oc = Chain(d), OracleChain(d)
+    n = 2500
+    q, dq, ddq, _ = _inputs(torch, d.n_inputs, n, 0x5EED0000 + 9)
+    Gr, br, ttr = oc.gram(_np(q), _np(dq), _np(ddq))
+    G, b, tt = (_np(x) for x in ch.regressorGram(q, dq, ddq))
+    scale = np.max(np.abs(Gr))
+    assert np.max(np.abs(G - Gr)) <= 1e-10 * scale, np.max(np.abs(G - Gr)) / scale
+    assert np.array_equal(G, G.T)
+    assert np.max(np.abs(b - br)) <= 1e-10 * np.max(np.abs(br))
+    assert abs(tt[0] - ttr) <= 1e-10 * ttr
+    # the materialised regressor (no folding there) gives the same normal equations
+    phi, tau = ch.getRegressor(q, dq, ddq, with_torque=True)
+    F = _np(phi).transpose(2, 0, 1).reshape(n * d.n_inputs, -1)  # (sample, row) x column
+    assert np.max(np.abs(F.T @ F - G)) <= 1e-10 * scale
+    assert np.max(np.abs(F.T @ _np(tau).T.reshape(-1) - b)) <= 1e-10 * np.max(np.abs(br))
+
+
 def test_edge_cases(chains, torch):
     d, ch, oc = chains("c6")
     # empty batch
