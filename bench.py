@@ -371,10 +371,24 @@ def main():
             peak = max(peaks64["dmma_m8n8k4"], peaks64["dfma"])
         ach = S * flop / (ms * 1e-3 / args.steps) / 1e12
         tps = ncu_traffic_per_sample(f"gram_fused_kernel<{d.n_joints}>:{args.chain}")
+        # what the kernel actually executes: joints that never move (fixed / not an input) are folded out of the chain (gram_fused.cu:
+        # fold_chain), and of the (P'+1)x(P'+1) augmented Gram matrix only the upper-triangular 8x8 tiles right of each row's first
+        # non-zero column are multiplied (one DMMA m8n8k4 = 512 flop per tile per 4 samples)
+        K = sum(1 for j in d.joints if j.input_index >= 0)
+        T = (10 * K + 1 + 7) // 8
+        dmma4 = sum((T - (10 * j) // 8) * (T - (10 * j) // 8 + 1) // 2 for j in range(K))
+        ex = dmma4 * 512 / 4
+        sps = S / (ms * 1e-3 / args.steps)
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None,
                 "traffic": (tps * S) if tps else None,
                 "peak_source": "own FP64 micro-benchmark on this GPU (max of DMMA m8n8k4 and DFMA); MEASURED_PEAKS.json has no FP64 figure",
-                "fp64_peaks_tflops": peaks64, "flop_per_sample": flop, "kernel": f"gram_fused_kernel<{d.n_joints}> (regressor generation + DMMA normal equations)"}
+                "fp64_peaks_tflops": peaks64, "flop_per_sample": flop,
+                "executed": {"moving_joints": K, "dmma_per_4_samples": dmma4, "dmma_flop_per_sample": ex, "dmma_tflops": sps * ex / 1e12,
+                             "dmma_frac_of_peak": (sps * ex / 1e12 / peak) if peak else None,
+                             "note": "achieved/frac use the ALGORITHMIC flops of the reference's dense n_act x 10nJ regressor (SYRK+GEMV convention, "
+                                     "SURVEY.md 8d); structural zeros and rigidly attached links are not multiplied, so frac can exceed 1. "
+                                     "The regressor generation (~5 kflop/sample of DFMA) shares the same FP64 datapath and is not counted here."},
+                "kernel": f"gram_fused_kernel<{K},slots> on the folded chain (regressor generation + DMMA normal equations)"}
     else:
         bytes_per_sample = 8 * (3 * n_in + P * n_in + n_in)          # 3552 B for C6
         ach = S * bytes_per_sample / (ms * 1e-3 / args.steps) / 1e9

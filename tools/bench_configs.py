@@ -109,7 +109,7 @@ def main():
     tt = torch.empty((1,), dtype=torch.float64, device=dev)
     ms = timed(lambda: check(lib.rdb_regressor_gram_batch(ch._h, ctypes.byref(smp), None, G.data_ptr(), b.data_ptr(), tt.data_ptr(), 0, stream())), args.steps)
     report("headline (fused Gram): C6 regressor+torque -> PhiT Phi / PhiT tau [gram_fused_kernel<7>]", S, ms, flop_per_sample=6 * 70 * 71 + 2 * 6 * 70,
-           note="flops: BLAS SYRK+GEMV convention; executed DMMA flops 18688/sample + ~5.6k generation")
+           note="flops: BLAS SYRK+GEMV convention; executed (folded chain, 6 moving joints): 13952 DMMA flop/sample + ~5 k generation")
     del q, dq, ddq, dddq
 
     # ---- config 3 / 4: C7
