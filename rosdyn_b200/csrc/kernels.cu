@@ -324,8 +324,62 @@ __device__ __forceinline__ void st_pose(double* p, int64_t plane0, int64_t ld, i
   }
 }
 
+// Per-joint state of the base-frame walker that must outlive the walk: the base-frame axis and the origin of every joint (the Jacobian needs
+// p_tool, the forward torque projection reads all earlier joints at every link).  In registers it is 6 doubles per joint -- with the torque
+// accumulators, more than the 128-register budget of 4 CTAs/SM holds, and the spills go through L1/L2 to DRAM (ncu: +11 % traffic).  The
+// unrolled torque kernels keep it in SHARED memory instead ([component][thread], conflict free, never written back): written once per joint,
+// read once per (joint, link) pair and once for the Jacobian.
+template <int CAP, bool SM>
+struct JointStore;
+template <int CAP>
+struct JointStore<CAP, false>
+{
+  V3 a[CAP], p[CAP];
+  __device__ __forceinline__ explicit JointStore(double*) {}
+  __device__ __forceinline__ void set(int j, V3 ab, V3 pj)
+  {
+    a[j] = ab;
+    p[j] = pj;
+  }
+  __device__ __forceinline__ V3 ab(int j) const { return a[j]; }
+  __device__ __forceinline__ V3 pj(int j) const { return p[j]; }
+};
+template <int CAP>
+struct JointStore<CAP, true>
+{
+  double* b;  // shared memory, already offset by threadIdx.x; component k of joint j at b[(6 j + k) RDB_BLOCK]
+  __device__ __forceinline__ explicit JointStore(double* base) : b(base) {}
+  __device__ __forceinline__ void set(int j, V3 ab, V3 pj)
+  {
+    double* q = b + 6 * j * RDB_BLOCK;
+    q[0] = ab.x;
+    q[RDB_BLOCK] = ab.y;
+    q[2 * RDB_BLOCK] = ab.z;
+    q[3 * RDB_BLOCK] = pj.x;
+    q[4 * RDB_BLOCK] = pj.y;
+    q[5 * RDB_BLOCK] = pj.z;
+  }
+  __device__ __forceinline__ V3 ab(int j) const
+  {
+    const double* q = b + 6 * j * RDB_BLOCK;
+    return v3(q[0], q[RDB_BLOCK], q[2 * RDB_BLOCK]);
+  }
+  __device__ __forceinline__ V3 pj(int j) const
+  {
+    const double* q = b + (6 * j + 3) * RDB_BLOCK;
+    return v3(q[0], q[RDB_BLOCK], q[2 * RDB_BLOCK]);
+  }
+};
+// shared-memory joint store: unrolled kernels that need the Jacobian or project the torque forward
+template <int NJ_T, unsigned MASK>
+struct KinSm
+{
+  static constexpr bool value = NJ_T > 0 && (MASK & (K_JAC | K_TORQUE)) != 0;
+  static constexpr size_t bytes = value ? sizeof(double) * 6 * NJ_T * RDB_BLOCK : 0;
+};
+
 template <int NJ_T, unsigned MASK, class ChainT>
-__device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, const KinOutDev& o, int64_t i)
+__device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, const KinOutDev& o, int64_t i, double* smp = nullptr)
 {
   constexpr int CAP = Cap<NJ_T>::value;
   const int nj = NJ_T > 0 ? NJ_T : C.nj;
@@ -351,7 +405,7 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
   V3 p = v3(0, 0, 0);
   Tw v = tw0(), a = tw0(), al = tw0(), an = tw0(), jf = tw0(), jl = tw0(), jn = tw0();
   // base-frame screw of joint j = [0; ab[j]] (revolute) / [ab[j]; 0] (prismatic) / 0 (fixed): one 3-vector + the joint type
-  V3 ab[cJac ? CAP : 1], pj[cJac ? CAP : 1];
+  JointStore<cJac ? CAP : 1, KinSm<NJ_T, MASK>::value> js(smp);
   double tau[(MASK & K_TORQUE) ? CAP : 1];
   constexpr int NT = NJ_T > 0 ? NJ_T : 1;
   double qv[NT], sv[NT], cv[NT];
@@ -362,6 +416,14 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     trig_all<NT>(qv, sv, cv);
   }
 
+  double dq_nx = 0.0, ddq_nx = 0.0, dddq_nx = 0.0;  // rates of the next link (unrolled kernels)
+  if (NJ_T > 0)
+  {
+    const int in0 = C.joint[0].in;
+    if (cVel) dq_nx = ld_in(in.dq, in0, in.ld, i);
+    if ((MASK & (K_DTWIST | K_DTWIST_LIN | K_TORQUE)) != 0 || cJer) ddq_nx = ld_in(in.ddq, in0, in.ld, i);
+    if ((MASK & (K_DDTWIST | K_DDTWIST_LIN)) != 0) dddq_nx = ld_in(in.dddq, in0, in.ld, i);
+  }
   // link 0 = base: identity pose, zero twists (primitives_impl.h:661-677, 697)
   if (wTl) st_pose(o.T_links, 0, ld, i, R, p);
   if (wV) st_tw(o.twist, 0, ld, i, v);
@@ -398,15 +460,31 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     for (int k = 0; k < 9; k++) R[k] = Rn[k];
     if (wTl) st_pose(o.T_links, (int64_t)12 * (l + 1), ld, i, R, p);
 
-    if (cJac)
-    {
-      ab[l] = axb;
-      pj[l] = p;
-    }
+    if (cJac) js.set(l, axb, p);
 
-    const double dql = (cVel) ? ld_in(in.dq, J.in, in.ld, i) : 0.0;
-    const double ddql = (MASK & (K_DTWIST | K_DTWIST_LIN | K_TORQUE)) || cJer ? ld_in(in.ddq, J.in, in.ld, i) : 0.0;
-    const double dddql = (MASK & (K_DDTWIST | K_DDTWIST_LIN)) ? ld_in(in.dddq, J.in, in.ld, i) : 0.0;
+    // the rates of link l were requested one link earlier (unrolled kernels): the DRAM latency hides behind the previous link's arithmetic
+    constexpr bool wantDD = (MASK & (K_DTWIST | K_DTWIST_LIN | K_TORQUE)) != 0 || cJer;
+    constexpr bool wantDDD = (MASK & (K_DDTWIST | K_DDTWIST_LIN)) != 0;
+    double dql, ddql, dddql;
+    if (NJ_T > 0)
+    {
+      dql = dq_nx;
+      ddql = ddq_nx;
+      dddql = dddq_nx;
+      if (l + 1 < NJ_T)
+      {
+        const int inn = C.joint[l + 1 < CAP ? l + 1 : 0].in;
+        if (cVel) dq_nx = ld_in(in.dq, inn, in.ld, i);
+        if (wantDD) ddq_nx = ld_in(in.ddq, inn, in.ld, i);
+        if (wantDDD) dddq_nx = ld_in(in.dddq, inn, in.ld, i);
+      }
+    }
+    else
+    {
+      dql = cVel ? ld_in(in.dq, J.in, in.ld, i) : 0.0;
+      ddql = wantDD ? ld_in(in.ddq, J.in, in.ld, i) : 0.0;
+      dddql = wantDDD ? ld_in(in.dddq, J.in, in.ld, i) : 0.0;
+    }
 
     Tw vxs = tw0();
     if (cVel)
@@ -479,8 +557,8 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
       {
         // s_j . dualTransl(w, p_j - p): the force part for a prismatic joint, the moment about the joint origin for a revolute one
         const int tj = C.joint[j].type;
-        if (tj == RDB_JOINT_REVOLUTE) tau[j] += dot(ab[j], cross_add(n, f, pj[j] - p));
-        else if (tj == RDB_JOINT_PRISMATIC) tau[j] += dot(ab[j], f);
+        if (tj == RDB_JOINT_REVOLUTE) tau[j] += dot(js.ab(j), cross_add(n, f, js.pj(j) - p));
+        else if (tj == RDB_JOINT_PRISMATIC) tau[j] += dot(js.ab(j), f);
       }
     }
   }
@@ -498,9 +576,10 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
       {
         const int tj = C.joint[j].type;
         const V3 z = v3(0, 0, 0);
-        const V3 lin = tj == RDB_JOINT_REVOLUTE ? cross(ab[j], p - pj[j]) : (tj == RDB_JOINT_PRISMATIC ? ab[j] : z);
+        const V3 abj = js.ab(j);
+        const V3 lin = tj == RDB_JOINT_REVOLUTE ? cross(abj, p - js.pj(j)) : (tj == RDB_JOINT_PRISMATIC ? abj : z);
         st3(o.jacobian, (int64_t)6 * r, ld, i, lin);
-        st3(o.jacobian, (int64_t)6 * r + 3, ld, i, tj == RDB_JOINT_REVOLUTE ? ab[j] : z);
+        st3(o.jacobian, (int64_t)6 * r + 3, ld, i, tj == RDB_JOINT_REVOLUTE ? abj : z);
       }
     }
   }
@@ -519,9 +598,10 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
 template <int NJ, unsigned MASK>
 __global__ void __launch_bounds__(RDB_BLOCK, RDB_KIN_MINB) kin_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const KinOutDev o)
 {
+  extern __shared__ double kin_sm[];
   const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
   if (i >= in.n) return;
-  kin_body<NJ, MASK>(C, in, o, i);
+  kin_body<NJ, MASK>(C, in, o, i, kin_sm + threadIdx.x);
 }
 
 template <unsigned MASK>
@@ -625,7 +705,7 @@ static cudaError_t launch_kin_mask(const ChainHost& ch, const SamplesDev& in, co
   {
 #define X(N)                                                                   \
   case N:                                                                      \
-    kin_kernel<N, MASK><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(ch.host), in, o); \
+    kin_kernel<N, MASK><<<grid, RDB_BLOCK, KinSm<N, MASK>::bytes, st>>>(narrow<N>(ch.host), in, o); \
     break;
     RDB_FAST_NJ(X)
 #undef X
