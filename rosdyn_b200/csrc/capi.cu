@@ -125,6 +125,7 @@ static rdb_status upload_model(ChainHost* ch)
   RDB_CUDA(cudaMemcpy(ch->dev, &ch->host, sizeof(ch->host), cudaMemcpyHostToDevice));
   cudaDeviceGetAttribute(&ch->sm_count, cudaDevAttrMultiProcessorCount, ch->device);
   ch->model_version++;
+  RDB_CUDA(fold_chain(*ch));
   return RDB_OK;
 }
 

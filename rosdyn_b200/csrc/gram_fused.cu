@@ -573,8 +573,8 @@ static void fold_param_map(const FoldXf& X, double* T)
   }
 }
 
-// (re)builds ch.gram.fold* for the current model; false when the folded chain is empty
-static cudaError_t fold_chain(ChainHost& ch)
+// (re)builds ch.gram.fold* for the current model (called by every model upload, capi.cu)
+cudaError_t fold_chain(ChainHost& ch)
 {
   GramWorkspace& w = ch.gram;
   if (w.fold_version == ch.model_version) return cudaSuccess;

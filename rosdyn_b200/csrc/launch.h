@@ -87,6 +87,8 @@ cudaError_t launch_components_regressor(const ChainHost& ch, const SamplesDev& i
 cudaError_t launch_components_torque(const ChainHost& ch, const SamplesDev& in, const ComponentParams& prm, double* torque, int64_t ld_out,
                                      int accumulate, cudaStream_t st);
 cudaError_t fp64_peak(int kind, int reps, double* tflops);
+// gram_fused.cu: the chain with its never-moving joints folded away (ch.gram.fold); rebuilt by every model upload
+cudaError_t fold_chain(ChainHost& ch);
 // gram_fused.cu: cudaErrorNotSupported when the chain does not fit the fused kernel
 cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
                               int accumulate, cudaStream_t st);
