@@ -2,25 +2,27 @@
 //
 //   G (+)= sum_s Phi_s^T Phi_s ,  b (+)= sum_s Phi_s^T tau_s ,  tau_sq (+)= sum_s tau_s^T tau_s
 //
-// Phi never touches HBM.  Per CTA (1 per SM, 8 MMA warps + 3 generator warps):
-//   * generator warps: one thread walks the chain of one sample (same link-frame recursion as dyn_kernel, kernels.cu) and writes the
-//     augmented regressor rows [Phi_row | tau_row] of its 32 samples into one of three shared-memory slots (only the structurally
-//     non-zero columns, XOR-swizzled, conflict free).  The inputs of the next group are requested BEFORE waiting for the slot, so the
-//     DRAM latency hides behind the consumers; sin/cos of all joints are evaluated up front (branch free), so the walk is one basic block.
-//   * MMA warps: consume a slot as soon as it is full.  The contraction index k = (sample, joint row); a k-step is 4 samples of one
-//     joint row, so the zero pattern of Phi (row of chain joint j is zero left of column 10 j) is known at compile time and whole 8x8
-//     tiles are skipped.  The upper-triangular tiles of the (P+1)x(P+1) augmented Gram matrix (45 for P = 70) stay in registers for
-//     the whole kernel: the two MMA warps of an SM sub-partition split them by tile-row parity (25 + 20 tiles), the four
-//     sub-partitions split the k-steps.  tcgen05 has no f64 kind: the FP64 tensor path of sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA).
-//   * slots cycle through shared-memory mbarriers (full / empty per slot).
+// Phi never touches HBM.  The kernel runs on the FOLDED chain (fold_chain below: joints that never move are merged into the constant
+// transform of the next moving joint, so every joint of the chain the kernel sees is an input and owns a row of Phi).  Per CTA (1 per SM):
+//   * generator warps (one per shared-memory slot): one thread walks the chain of one sample (same link-frame recursion as dyn_kernel,
+//     kernels.cu) and writes the augmented regressor rows [Phi_row | tau_row] of its 32 samples into its slot (only the structurally
+//     non-zero columns, XOR-swizzled, conflict free).  The inputs of the next group are requested BEFORE waiting for the slot, so the DRAM
+//     latency hides behind the consumers; sin/cos of all joints are evaluated up front (branch free), so the walk is one basic block.
+//   * MMA warps: consume a slot as soon as it is full.  The contraction index k = (sample, joint row); a k-step is 4 samples of one joint
+//     row, so the zero pattern of Phi (row of chain joint j is zero left of column 10 j) is known at compile time and whole 8x8 tiles are
+//     skipped.  The upper-triangular tiles of the (P+1)x(P+1) augmented Gram matrix stay in registers for the whole kernel; the four SM
+//     sub-partitions split the k-steps of a slot, GF_TSPLIT warps per sub-partition split the tile rows by parity.  The k-steps of a slot
+//     are fully unrolled and software pipelined: the fragments of step n+1 are loaded while the DMMAs of step n issue.
+//     tcgen05 has no f64 kind: the FP64 tensor path of sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA).
+//   * slots cycle through shared-memory mbarriers (full / empty per slot); as many slots as fit the 227 KB (3 for 7 joints, 4 below).
 // Per-CTA partials are summed in a fixed order by gram_fused_reduce_kernel (bit-reproducible for a given n).
 //
-// What bounds it (ncu, profiles/r01_gram_fused_v2_ncu.txt): DMMA and DFMA share ONE FP64 datapath; a DMMA occupies it for 16 cycles,
-// a DFMA for 2, and the warp scheduler grants it per instruction, so while the MMA warps work on a slot the generators crawl
-// (38 % of their time is math-pipe throttle) and the two phases effectively alternate.  The generator alone is latency bound (one warp
-// per 32 samples; the 227 KB of shared memory hold 96 samples in flight, which is what limits the generator warps to 3).  Splitting the
-// rows of a slot over more generator warps (GF_RSPLIT > 1) was measured SLOWER: each group is its own unrolled code and the kernel then
-// overflows the instruction cache (sm__icc hit rate 86 % -> 53 %).  Per-row slot release and an uneven k-split were also measured slower.
+// What bounds it (ncu, profiles/r01_gram_fused_v3_ncu.txt): DMMA and DFMA share ONE FP64 datapath; a DMMA occupies it for 16 cycles, a DFMA
+// for 2 (tools/micro/dfma_latency.cu), and the warp scheduler grants it per instruction, so while the MMA warps work on a slot the generators
+// crawl and the two phases effectively alternate; the generator alone is latency bound (one warp per 32 samples).  Measured slower and
+// removed: splitting the rows of a slot over several generator warps (each group its own unrolled code: instruction-cache misses), two lanes
+// per sample with 14 warps (the 16 K registers of a sub-partition cap 4 warps at 128 registers: the walker spills), per-row slot release,
+// an uneven k-split between the sub-partitions.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -36,62 +38,19 @@ namespace rdb
 #ifndef GF_TSPLIT
 #define GF_TSPLIT 2
 #endif
-constexpr int GF_KSPLIT = 4;                       // MMA warps that share the k-steps of a slot (one per SM sub-partition)
-constexpr int GF_TS = GF_TSPLIT;                   // 1: each MMA warp owns all tiles; 2: two warps per sub-partition split the tile rows by parity
+constexpr int GF_KSPLIT = 4;      // MMA warps that share the k-steps of a slot (one per SM sub-partition)
+constexpr int GF_TS = GF_TSPLIT;  // 1: each MMA warp owns all tiles; 2: two warps per sub-partition split the tile rows by parity
 constexpr int GF_MMA_WARPS = GF_KSPLIT * GF_TS;
-constexpr int GF_MAX_SLOTS = 4;  // 32-sample slots in shared memory: as many as fit the 227 KB (3 for a 7-joint chain, 4 from 6 joints down);
-                                 // 8 MMA + 4 generator warps = 3 warps per SM sub-partition is also what the 168-register budget allows
-#ifndef GF_RSPLIT
-#define GF_RSPLIT 1
-#endif
-#ifndef GF_UNEVEN
-#define GF_UNEVEN 0  // 1: sub-partition 3 (no generator warp) takes 3 of the 8 k-steps -- measured much slower (it becomes the critical path)
-#endif
-constexpr int GF_MAXG = 3;       // most row groups (generator warps) per slot
+constexpr int GF_MAX_SLOTS = 4;   // 32-sample slots in shared memory: as many as fit the 227 KB (3 for a 7-joint chain, 4 from 6 joints down);
+                                  // 8 MMA + 4 generator warps = 3 warps per SM sub-partition is also what the 168-register budget allows
 constexpr int GF_BAR_REDUCE = 1;  // named barrier of the final k-split reduction (0 is __syncthreads)
-
-// Row groups.  The generator of a slot is latency bound (one warp per 32 samples, ~2.8 k dependent-ish DP instructions), and shared
-// memory allows only GF_SLOTS x 32 samples in flight, so the rows of Phi of one slot are split between NG generator warps: warp g walks
-// the whole chain but carries the unit twists of, projects on and stores only the chain joints [bound(g), bound(g+1)).  Each (slot, group)
-// has its own full/empty mbarrier pair, so a generator never waits for the other groups of its slot.
-__host__ __device__ constexpr int gf_groups(int NJ) { return NJ >= 4 ? GF_RSPLIT : 1; }
-__host__ __device__ constexpr int gf_pairs_before(int NJ, int b)  // (joint, link) pairs of the rows < b
-{
-  int c = 0;
-  for (int j = 0; j < b; j++) c += NJ - j;
-  return c;
-}
-__host__ __device__ constexpr int gf_bound(int NJ, int NG, int g)  // first chain joint of group g (nearest to an even split of the pairs)
-{
-  if (g <= 0) return 0;
-  if (g >= NG) return NJ;
-  const int total = gf_pairs_before(NJ, NJ);
-  int best = 1, bestd = 1 << 30;
-  for (int b = 1; b < NJ; b++)
-  {
-    int d = gf_pairs_before(NJ, b) * NG - total * g;
-    if (d < 0) d = -d;
-    if (d < bestd)
-    {
-      bestd = d;
-      best = b;
-    }
-  }
-  return best;
-}
-
-struct GramRows
-{
-  int32_t base[8];      // offset (doubles) of the row of chain joint j inside a slot, -1 when the joint is not an input
-  int32_t slot_doubles;  // doubles per slot
-};
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void dmma884f(double& d0, double& d1, double a, double b)
 {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-// mbarriers in shared memory (one full / one empty per (slot, row group)); arrive = release.cta, wait = acquire.cta
+// mbarriers in shared memory (one full / one empty per slot); arrive = release.cta, wait = acquire.cta
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count)
 {
@@ -112,6 +71,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
       : "memory");
 }
 
+// geometry of the augmented Gram matrix and of a slot for a (folded) chain of NJ joints, all of them inputs
+template <int NJ>
+struct GramGeom
+{
+  static constexpr int P = 10 * NJ;
+  static constexpr int T = (P + 1 + 7) / 8;   // tile columns of the augmented matrix
+  static constexpr int NT = T * (T + 1) / 2;  // upper-triangular tiles
+  static constexpr int KPW = 8 / GF_KSPLIT;   // k-steps (4 samples) of one MMA warp per joint row and slot
+  static constexpr int NSTEPS = NJ * KPW;     // k-steps of one MMA warp per slot
+  __host__ __device__ static constexpr int threads(int slots) { return 32 * (GF_MMA_WARPS + slots); }
+  // offset (doubles) of the row of joint j inside a slot: [column - 10 j][sample], only the columns 10 j .. P (tau) are stored
+  __host__ __device__ static constexpr int rowbase(int j)
+  {
+    int o = 0;
+    for (int i = 0; i < j; i++) o += (P + 1 - 10 * i) * 32;
+    return o;
+  }
+  static constexpr int SLOT_DOUBLES = rowbase(NJ);
+  __host__ __device__ static constexpr int tile(int I, int J) { return I * T - I * (I - 1) / 2 + (J - I); }
+  // tile rows owned by an MMA warp: all (TS == 1) or the rows of parity `par` (TS == 2)
+  __host__ __device__ static constexpr bool owns(int I, int ts, int par) { return ts == 1 || (I & 1) == par; }
+  __host__ __device__ static constexpr int ntiles(int ts, int par)
+  {
+    int n = 0;
+    for (int I = 0; I < T; I++)
+      if (owns(I, ts, par)) n += T - I;
+    return n;
+  }
+  __host__ __device__ static constexpr int local(int I, int J, int ts, int par)
+  {
+    int n = 0;
+    for (int K = 0; K < I; K++)
+      if (owns(K, ts, par)) n += T - K;
+    return n + (J - I);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------- generator
 template <int NJ>
 struct GenIn
@@ -130,22 +126,15 @@ __device__ __forceinline__ void gen_load(const ChainDev<NJ>& C, const SamplesDev
   }
 }
 
+// One sample per lane: all rows of getRegressor (+ getJointTorque) of sample i written to the slot.
 template <int NJ>
-__device__ __forceinline__ void gen_trig(GenIn<NJ>& x)
+__device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GenIn<NJ>& x, const SamplesDev& in, const double* __restrict__ tau_meas,
+                                              double* __restrict__ slot, int64_t i, int lane)
 {
-  trig_all<NJ>(x.q, x.sv, x.cv);
-}
-
-// One sample per lane: the rows [J0, J1) of getRegressor (+ getJointTorque) of sample i written to the slot.
-// The walk (getTwist / getDTwist moved to link axes) covers every link; unit twists are carried only for the joints of this group.
-template <int NJ, int J0, int J1>
-__device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramRows& rows, const GenIn<NJ>& x, const SamplesDev& in,
-                                              const double* __restrict__ tau_meas, double* __restrict__ slot, int64_t i, int lane)
-{
-  constexpr int P = 10 * NJ;
-  constexpr int NR = J1 - J0 > 0 ? J1 - J0 : 1;
-  V3 U[NR], S[NR];
-  double tau[NR];
+  using G = GramGeom<NJ>;
+  constexpr int P = G::P;
+  V3 U[NJ], S[NJ];
+  double tau[NJ];
   V3 v = v3(0, 0, 0), w = v3(0, 0, 0), a = v3(0, 0, 0), al = v3(0, 0, 0);
   V3 g = v3(C.g);
 #pragma unroll
@@ -181,27 +170,21 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramR
     const V3 xa = cross(w, ss);
     a = axpy(axpy(a, xl, dql), su, ddql);
     al = axpy(axpy(al, xa, dql), ss, ddql);
-    if (l < J0) continue;  // the rows of this group have no entries in the column blocks of earlier links
 #pragma unroll
-    for (int j = J0; j < J1; j++)
-      if (j < l)
-      {
-        U[j - J0] = rotT(R, cross_add(U[j - J0], S[j - J0], t));
-        S[j - J0] = rotT(R, S[j - J0]);
-      }
-    if (l < J1)
+    for (int j = 0; j < l; j++)
     {
-      U[l - J0] = su;
-      S[l - J0] = ss;
-      tau[l - J0] = 0.0;
+      U[j] = rotT(R, cross_add(U[j], S[j], t));
+      S[j] = rotT(R, S[j]);
     }
+    U[l] = su;
+    S[l] = ss;
+    tau[l] = 0.0;
     const double* Pl = C.link[l].pi;
     const V3 fm = cross_add(a - g, w, v);
 #pragma unroll
-    for (int j = J0; j < J1; j++)
+    for (int j = 0; j <= l; j++)
     {
-      if (j > l) continue;
-      const V3 u = U[j - J0], s = S[j - J0];
+      const V3 u = U[j], s = S[j];
       const double e0 = dot(u, fm);
       const V3 wu = cross(w, u);
       const V3 h = cross_add(cross_add(cross(u, al), w, wu), fm, s);
@@ -218,155 +201,92 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramR
       e[8] = fma(s.y, al.z, fma(s.z, al.y, fma(rho.y, w.z, rho.z * w.y)));
       e[9] = fma(s.z, al.z, rho.z * w.z);
       // tau_j += Phi_{j,l,:} . pi_l in two independent chains
-      double t0 = tau[j - J0], t1 = e[1] * Pl[1];
+      double t0 = tau[j], t1 = e[1] * Pl[1];
 #pragma unroll
       for (int p = 0; p < 10; p += 2) t0 = fma(e[p], Pl[p], t0);
 #pragma unroll
       for (int p = 3; p < 10; p += 2) t1 = fma(e[p], Pl[p], t1);
-      tau[j - J0] = t0 + t1;
-      const int rb = rows.base[j];
-      if (rb >= 0)
-      {
-        double* o = slot + rb + (10 * (l - j)) * 32;
+      tau[j] = t0 + t1;
+      double* o = slot + G::rowbase(j) + (10 * (l - j)) * 32;
 #pragma unroll
-        for (int p = 0; p < 10; p++) o[p * 32 + (lane ^ (4 * ((10 * l + p) & 3)))] = e[p];
-      }
+      for (int p = 0; p < 10; p++) o[p * 32 + (lane ^ (4 * ((10 * l + p) & 3)))] = e[p];
     }
   }
 #pragma unroll
-  for (int j = J0; j < J1; j++)
+  for (int j = 0; j < NJ; j++)
   {
-    const int rb = rows.base[j];
-    if (rb >= 0)
-    {
-      const double tv = tau_meas ? __ldcs(tau_meas + (int64_t)C.joint[j].in * in.ld + i) : tau[j - J0];
-      slot[rb + (P - 10 * j) * 32 + (lane ^ (4 * (P & 3)))] = tv;
-    }
+    const double tv = tau_meas ? __ldcs(tau_meas + (int64_t)C.joint[j].in * in.ld + i) : tau[j];
+    slot[G::rowbase(j) + (P - 10 * j) * 32 + (lane ^ (4 * (P & 3)))] = tv;
   }
 }
 
-// lanes past the end of the batch (last group only): their rows of the group [J0, J1) become exact zeros
-template <int NJ, int J0, int J1>
-__device__ __noinline__ void gram_zero_lane(const GramRows& rows, double* __restrict__ slot, int lane)
+// lanes past the end of the batch (last group only): their rows become exact zeros
+template <int NJ>
+__device__ __noinline__ void gram_zero_lane(double* __restrict__ slot, int lane)
 {
-  constexpr int P = 10 * NJ;
-  for (int j = J0; j < J1; j++)
-  {
-    const int rb = rows.base[j];
-    if (rb < 0) continue;
-    for (int c = 10 * j; c <= P; c++) slot[rb + (c - 10 * j) * 32 + (lane ^ (4 * (c & 3)))] = 0.0;
-  }
+  using G = GramGeom<NJ>;
+  for (int j = 0; j < NJ; j++)
+    for (int c = 10 * j; c <= G::P; c++) slot[G::rowbase(j) + (c - 10 * j) * 32 + (lane ^ (4 * (c & 3)))] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------- MMA side
-template <int NJ>
-struct GramGeom
-{
-  static constexpr int P = 10 * NJ;
-  static constexpr int T = (P + 1 + 7) / 8;       // tile columns of the augmented matrix
-  static constexpr int NT = T * (T + 1) / 2;      // upper-triangular tiles
-  static constexpr int NG = gf_groups(NJ);        // row groups = generator warps per slot
-  __host__ __device__ static constexpr int threads(int slots) { return 32 * (GF_MMA_WARPS + slots * NG); }
-  __host__ __device__ static constexpr int tile(int I, int J) { return I * T - I * (I - 1) / 2 + (J - I); }
-  // tile rows owned by an MMA warp: all (TS == 1) or the rows of parity `par` (TS == 2)
-  __host__ __device__ static constexpr bool owns(int I, int ts, int par) { return ts == 1 || (I & 1) == par; }
-  __host__ __device__ static constexpr int ntiles(int ts, int par)
-  {
-    int n = 0;
-    for (int I = 0; I < T; I++)
-      if (owns(I, ts, par)) n += T - I;
-    return n;
-  }
-  __host__ __device__ static constexpr int local(int I, int J, int ts, int par)
-  {
-    int n = 0;
-    for (int K = 0; K < I; K++)
-      if (owns(K, ts, par)) n += T - K;
-    return n + (J - I);
-  }
-};
-
-// the k-steps of the rows [J0, J1) of one slot that belong to k-split index `ks`, for the tile rows this warp owns
-template <int NJ, int PAR, int J0, int J1>
-__device__ __forceinline__ void gram_consume(const GramRows& rows, const double* __restrict__ slot, int k0, int k1, int lane,
-                                             double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
+// B fragments of one k-step (4 samples of joint row J, k-step kk of the slot): lane (g, t) holds column 8 I + g of sample 4 kk + t
+template <int NJ, int J>
+__device__ __forceinline__ void gram_load_frags(const double* __restrict__ slot, int kk, int lane, double (&b)[GramGeom<NJ>::T])
 {
   using G = GramGeom<NJ>;
-  constexpr int P = G::P, T = G::T;
+  constexpr int P = G::P, T = G::T, c0 = 10 * J, I0 = c0 / 8;
   const int g = lane >> 2, t = lane & 3;
-  const int swz = 4 * (g & 3);
+  const double* rowp = slot + G::rowbase(J) + ((4 * kk + t) ^ (4 * (g & 3)));
 #pragma unroll
-  for (int j = J0; j < J1; j++)
+  for (int I = 0; I < T; I++)
   {
-    const int rb = rows.base[j];
-    if (rb < 0) continue;
-    const int c0 = 10 * j;
-    const int I0 = c0 / 8;
-    const double* rowp = slot + rb;
-#pragma unroll 1
-    for (int kk = k0; kk < k1; kk++)
-    {
-      const int s = 4 * kk + t;
-      double b[T];
-#pragma unroll
-      for (int J = 0; J < T; J++)
-      {
-        if (J < I0) continue;
-        const int col = 8 * J + g;
-        const bool all_valid = (8 * J >= c0) && (8 * J + 7 <= P);
-        if (all_valid || (col >= c0 && col <= P)) b[J] = rowp[(col - c0) * 32 + (s ^ swz)];
-        else b[J] = 0.0;
-      }
-#pragma unroll
-      for (int I = 0; I < T; I++)
-      {
-        if (I < I0 || !G::owns(I, GF_TS, PAR)) continue;
-#pragma unroll
-        for (int J = I; J < T; J++) dmma884f(acc[G::local(I, J, GF_TS, PAR)][0], acc[G::local(I, J, GF_TS, PAR)][1], b[I], b[J]);
-      }
-    }
+    if (I < I0) continue;
+    const int col = 8 * I + g;
+    const bool all_valid = (8 * I >= c0) && (8 * I + 7 <= P);
+    if (all_valid || (col >= c0 && col <= P)) b[I] = rowp[(col - c0) * 32];
+    else b[I] = 0.0;
   }
+}
+template <int NJ, int PAR, int J>
+__device__ __forceinline__ void gram_mma_step(const double (&b)[GramGeom<NJ>::T], double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
+{
+  using G = GramGeom<NJ>;
+  constexpr int T = G::T, I0 = (10 * J) / 8;
+#pragma unroll
+  for (int I = 0; I < T; I++)
+  {
+    if (I < I0 || !G::owns(I, GF_TS, PAR)) continue;
+#pragma unroll
+    for (int K = I; K < T; K++) dmma884f(acc[G::local(I, K, GF_TS, PAR)][0], acc[G::local(I, K, GF_TS, PAR)][1], b[I], b[K]);
+  }
+}
+// k-steps STEP.. of this warp in one slot; step = (joint row, k-step of the warp); the fragments of the next step are in flight while the
+// DMMAs of the current one issue
+template <int NJ, int PAR, int STEP>
+__device__ __forceinline__ void gram_consume_steps(const double* __restrict__ slot, int ks, int lane, const double (&bcur)[GramGeom<NJ>::T],
+                                                   double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
+{
+  using G = GramGeom<NJ>;
+  constexpr int J = STEP / G::KPW;
+  if constexpr (STEP + 1 < G::NSTEPS)
+  {
+    double bnext[G::T];
+    gram_load_frags<NJ, (STEP + 1) / G::KPW>(slot, ks * G::KPW + (STEP + 1) % G::KPW, lane, bnext);
+    gram_mma_step<NJ, PAR, J>(bcur, acc);
+    gram_consume_steps<NJ, PAR, STEP + 1>(slot, ks, lane, bnext, acc);
+  }
+  else
+    gram_mma_step<NJ, PAR, J>(bcur, acc);
 }
 
 struct GramBars
 {
-  uint64_t full[GF_MAX_SLOTS][GF_MAXG], empty[GF_MAX_SLOTS][GF_MAXG];
+  uint64_t full[GF_MAX_SLOTS], empty[GF_MAX_SLOTS];
 };
 
-template <int NJ, int SLOTS, int PAR, int GRP>
-__device__ __forceinline__ void gram_consume_groups(const GramRows& rows, const double* slot, GramBars* bars, int s, uint32_t parity, bool again,
-                                                    int ks, int lane, int dbg, double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
-{
-  using G = GramGeom<NJ>;
-  if constexpr (GRP < G::NG)
-  {
-    mbar_wait(&bars->full[s][GRP], parity);
-    // k-steps (4 samples each) of this warp in this slot.  The generator warps sit on SM sub-partitions 0..2 and share the FP64 datapath
-    // with the MMA warps there, sub-partition 3 has MMA warps only: it takes 3 of the 8 k-steps, the others 2, 2 and 1 (rotating with the slot)
-    int k0, k1;
-    if (GF_UNEVEN && SLOTS == 3 && GF_KSPLIT == 4)
-    {
-      const int o = ks == 3 ? 3 : (ks - s + 3) % 3;
-      k0 = o == 3 ? 0 : (o == 0 ? 3 : (o == 1 ? 5 : 7));
-      k1 = o == 3 ? 3 : (o == 0 ? 5 : (o == 1 ? 7 : 8));
-    }
-    else
-    {
-      k0 = ks * (8 / GF_KSPLIT);
-      k1 = k0 + 8 / GF_KSPLIT;
-    }
-    if (!(dbg & 2)) gram_consume<NJ, PAR, gf_bound(NJ, G::NG, GRP), gf_bound(NJ, G::NG, GRP + 1)>(rows, slot, k0, k1, lane, acc);
-    if (again)  // the generator will come back for this slot
-    {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->empty[s][GRP]);
-    }
-    gram_consume_groups<NJ, SLOTS, PAR, GRP + 1>(rows, slot, bars, s, parity, again, ks, lane, dbg, acc);
-  }
-}
-
 template <int NJ, int SLOTS, int PAR>
-__device__ __forceinline__ void gram_mma_role(const GramRows& rows, const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane, int dbg)
+__device__ __forceinline__ void gram_mma_role(const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane, int dbg)
 {
   using G = GramGeom<NJ>;
   constexpr int NTP = G::ntiles(GF_TS, PAR);
@@ -382,7 +302,19 @@ __device__ __forceinline__ void gram_mma_role(const GramRows& rows, const Sample
     for (int s = 0; s < SLOTS; s++)
     {
       if (base + s >= ngroups) break;
-      gram_consume_groups<NJ, SLOTS, PAR, 0>(rows, smem + (size_t)s * rows.slot_doubles, bars, s, parity, base + s + stride < ngroups, ks, lane, dbg, acc);
+      const double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
+      mbar_wait(&bars->full[s], parity);
+      if (!(dbg & 2))
+      {
+        double b0[G::T];
+        gram_load_frags<NJ, 0>(slot, ks * G::KPW, lane, b0);
+        gram_consume_steps<NJ, PAR, 0>(slot, ks, lane, b0, acc);
+      }
+      if (base + s + stride < ngroups)  // the generator will come back for this slot
+      {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->empty[s]);
+      }
     }
   }
   // fixed-order reduction over the k-split warps that own the same tiles, into shared memory (the slots are dead by now)
@@ -418,47 +350,37 @@ __device__ __forceinline__ void gram_mma_role(const GramRows& rows, const Sample
   }
 }
 
-template <int NJ, int SLOTS, int GRP>
-__device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const GramRows& rows, const SamplesDev& in, const double* __restrict__ tau_meas,
-                                              double* smem, GramBars* bars, int gen_id, int lane, int dbg)
+template <int NJ, int SLOTS>
+__device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const SamplesDev& in, const double* __restrict__ tau_meas, double* smem,
+                                              GramBars* bars, int s, int lane, int dbg)
 {
   using G = GramGeom<NJ>;
-  if constexpr (GRP < G::NG)
+  double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
+  const int64_t ngroups = (in.n + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * SLOTS;
+  uint32_t parity = 1;  // first wait on an un-arrived barrier with parity 1 returns at once ("previous phase complete")
+  for (int64_t grp = (int64_t)blockIdx.x * SLOTS + s; grp < ngroups; grp += stride, parity ^= 1)
   {
-    if (gen_id % G::NG == GRP)
+    // the inputs are requested BEFORE waiting for the slot: the DRAM latency hides behind the consumers' work on the previous group
+    const int64_t i = grp * 32 + lane;
+    GenIn<NJ> cur;
+    gen_load<NJ>(C, in, min(i, in.n - 1), cur);
+    trig_all<NJ>(cur.q, cur.sv, cur.cv);
+    mbar_wait(&bars->empty[s], parity);  // consumers released the slot
+    if (!(dbg & 1))
     {
-      const int s = gen_id / G::NG;
-      double* slot = smem + (size_t)s * rows.slot_doubles;
-      const int64_t ngroups = (in.n + 31) / 32;
-      const int64_t stride = (int64_t)gridDim.x * SLOTS;
-      constexpr int J0 = gf_bound(NJ, G::NG, GRP), J1 = gf_bound(NJ, G::NG, GRP + 1);
-      uint32_t parity = 1;  // first wait on an un-arrived barrier with parity 1 returns at once ("previous phase complete")
-      for (int64_t grp = (int64_t)blockIdx.x * SLOTS + s; grp < ngroups; grp += stride, parity ^= 1)
-      {
-        // the inputs are requested BEFORE waiting for the slot: the DRAM latency hides behind the consumers' work on the previous group
-        const int64_t i = grp * 32 + lane;
-        GenIn<NJ> cur;
-        gen_load<NJ>(C, in, min(i, in.n - 1), cur);
-        gen_trig<NJ>(cur);
-        mbar_wait(&bars->empty[s][GRP], parity);  // consumers released this part of the slot
-        if (!(dbg & 1))
-        {
-          gram_generate<NJ, J0, J1>(C, rows, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
-          if (i >= in.n) gram_zero_lane<NJ, J0, J1>(rows, slot, lane);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->full[s][GRP]);
-      }
+      gram_generate<NJ>(C, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
+      if (i >= in.n) gram_zero_lane<NJ>(slot, lane);
     }
-    else
-      gram_gen_role<NJ, SLOTS, GRP + 1>(C, rows, in, tau_meas, smem, bars, gen_id, lane, dbg);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars->full[s]);
   }
 }
 
 template <int NJ, int SLOTS>
 __global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
-    gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const __grid_constant__ GramRows rows, const SamplesDev in,
-                      const double* __restrict__ tau_meas, double* __restrict__ partial, const int dbg)
+    gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const double* __restrict__ tau_meas, double* __restrict__ partial,
+                      const int dbg)
 {
   using G = GramGeom<NJ>;
   extern __shared__ __align__(16) double smem[];
@@ -467,25 +389,24 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
   if (threadIdx.x == 0)
   {
     for (int s = 0; s < SLOTS; s++)
-      for (int g = 0; g < GF_MAXG; g++)
-      {
-        mbar_init(&bars.full[s][g], 1);             // lane 0 of the generator warp, after __syncwarp
-        mbar_init(&bars.empty[s][g], GF_MMA_WARPS);  // lane 0 of every MMA warp
-      }
+    {
+      mbar_init(&bars.full[s], 1);              // lane 0 of the generator warp, after __syncwarp
+      mbar_init(&bars.empty[s], GF_MMA_WARPS);  // lane 0 of every MMA warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // group of (iteration it, CTA, slot s): (it*gridDim.x + blockIdx.x)*SLOTS + s ; generator warp (s, g) writes the rows of group g
+  // group of (iteration it, CTA, slot s): (it*gridDim.x + blockIdx.x)*SLOTS + s ; generator warp s fills slot s
   if (warp >= GF_MMA_WARPS)
   {
-    gram_gen_role<NJ, SLOTS, 0>(C, rows, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
+    gram_gen_role<NJ, SLOTS>(C, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
     return;
   }
   // ------------------------------------------------ MMA warps: k-split index = warp % 4 (its SM sub-partition), tile-row parity = warp / 4
   const int mma_id = warp;
   const int ks = mma_id % GF_KSPLIT;
-  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, SLOTS, 0>(rows, in, smem, &bars, ks, lane, dbg);
-  else gram_mma_role<NJ, SLOTS, 1>(rows, in, smem, &bars, ks, lane, dbg);
+  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, SLOTS, 0>(in, smem, &bars, ks, lane, dbg);
+  else gram_mma_role<NJ, SLOTS, 1>(in, smem, &bars, ks, lane, dbg);
   double* out = partial + (size_t)blockIdx.x * G::NT * 64;
   for (int k = mma_id * 32 + lane; k < G::NT * 64; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
 }
@@ -693,11 +614,11 @@ static ChainDev<NJ> narrow_g(const ChainDev<RDB_MAX_JOINTS>& h)
 }
 
 template <int NJ, int SLOTS>
-static cudaError_t launch_fused_nj(ChainHost& ch, const GramRows& rows, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs,
-                                   double* tau_sq, int accumulate, cudaStream_t st)
+static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
+                                   int accumulate, cudaStream_t st)
 {
   using G = GramGeom<NJ>;
-  const size_t smem = sizeof(double) * (size_t)std::max(rows.slot_doubles * SLOTS, G::NT * 64);
+  const size_t smem = sizeof(double) * (size_t)std::max(G::SLOT_DOUBLES * SLOTS, G::NT * 64);
   {
     cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -715,7 +636,7 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const GramRows& rows, const Sa
     if (e != cudaSuccess) return e;
     ch.gram.fused_bytes = need;
   }
-  gram_fused_kernel<NJ, SLOTS><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), rows, in, tau_meas, ch.gram.fused_partials, dbg);
+  gram_fused_kernel<NJ, SLOTS><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), in, tau_meas, ch.gram.fused_partials, dbg);
   count_launch();
   if (ch.gram.fold_identity)
   {
@@ -738,48 +659,22 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const GramRows& rows, const Sa
   return cudaGetLastError();
 }
 
+// slots that fit the shared memory of an SM (227 KB minus 1 KB of barriers / static data)
+template <int NJ>
+constexpr int gf_slots()
+{
+  return std::min<int>(GF_MAX_SLOTS, (int)((227 * 1024 - 1024) / (sizeof(double) * GramGeom<NJ>::SLOT_DOUBLES)));
+}
+
 // returns cudaErrorNotSupported when the chain does not fit the fused kernel (caller falls back to the general pipeline)
 cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
                               int accumulate, cudaStream_t st)
 {
-  if (in.n <= 0) return cudaErrorNotSupported;
-  static const bool no_fold = [] { const char* e = getenv("RDB_GRAM_NOFOLD"); return e && e[0] == '1'; }();  // timing experiments only
-  if (no_fold)
+  if (in.n <= 0 || ch.gram.fold_version != ch.model_version) return cudaErrorNotSupported;
+  switch (ch.gram.fold.nj)  // moving joints; every joint of the folded chain is an input
   {
-    ch.gram.fold = ch.host;
-    ch.gram.fold_identity = true;
-    ch.gram.fold_version = ~0ull;
-  }
-  else
-  {
-    cudaError_t e = fold_chain(ch);
-    if (e != cudaSuccess) return e;
-  }
-  const ChainDev<RDB_MAX_JOINTS>& F = ch.gram.fold;
-  const int nj = F.nj;
-  if (nj < 1 || nj > 7) return cudaErrorNotSupported;
-  GramRows rows;
-  int off = 0;
-  const int P = 10 * nj;
-  for (int j = 0; j < 8; j++)
-  {
-    rows.base[j] = -1;
-    if (j < nj && F.joint[j].in >= 0)
-    {
-      rows.base[j] = off;
-      off += (P + 1 - 10 * j) * 32;
-    }
-  }
-  rows.slot_doubles = off;
-  const size_t budget = 227 * 1024 - 1024;
-  if (off == 0 || sizeof(double) * (size_t)off * 3 > budget) return cudaErrorNotSupported;
-  const bool four = sizeof(double) * (size_t)off * 4 <= budget;
-  switch (nj)
-  {
-#define X(N)                                                                                                    \
-  case N:                                                                                                       \
-    return four ? launch_fused_nj<N, 4>(ch, rows, in, tau_meas, gram, rhs, tau_sq, accumulate, st)             \
-                : launch_fused_nj<N, 3>(ch, rows, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
+#define X(N) \
+  case N: return launch_fused_nj<N, gf_slots<N>()>(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
     X(1) X(2) X(3) X(4) X(5) X(6) X(7)
 #undef X
   }
