@@ -257,6 +257,9 @@ def main():
     dev = torch.device("cuda", local)
     old_affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO writes it to stdout) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and "NCCL_DEBUG_FILE" not in os.environ:
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
 
     d = fixtures.by_name(args.chain)

@@ -127,7 +127,10 @@ __device__ __forceinline__ void gen_load(const ChainDev<NJ>& C, const SamplesDev
 }
 
 // One sample per lane: all rows of getRegressor (+ getJointTorque) of sample i written to the slot.
-template <int NJ>
+// REV: every joint of the (folded) chain is revolute -- the usual arm.  The joint type is then a compile-time fact: no type selects, the
+// linear half of every joint screw is an exact zero that is never multiplied, and the projection of a link on its own joint (unit twist
+// [0; axis] at birth) loses its linear terms.
+template <int NJ, bool REV>
 __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GenIn<NJ>& x, const SamplesDev& in, const double* __restrict__ tau_meas,
                                               double* __restrict__ slot, int64_t i, int lane)
 {
@@ -144,7 +147,7 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GenIn
     const double dql = x.dq[l], ddql = x.ddq[l];
     double R[9];
     V3 t = v3(J.t);
-    if (J.type == RDB_JOINT_REVOLUTE)
+    if (REV || J.type == RDB_JOINT_REVOLUTE)
     {
       const double c1 = 1.0 - x.cv[l];
 #pragma unroll
@@ -157,19 +160,28 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GenIn
       if (J.type == RDB_JOINT_PRISMATIC) t = axpy(t, v3(J.axp), x.q[l]);
     }
     const V3 axj = v3(J.ax);
-    const V3 su = (J.type == RDB_JOINT_PRISMATIC) ? axj : v3(0, 0, 0);
-    const V3 ss = (J.type == RDB_JOINT_REVOLUTE) ? axj : v3(0, 0, 0);
+    const V3 su = (!REV && J.type == RDB_JOINT_PRISMATIC) ? axj : v3(0, 0, 0);
+    const V3 ss = (REV || J.type == RDB_JOINT_REVOLUTE) ? axj : v3(0, 0, 0);
     v = rotT(R, cross_add(v, w, t));
     w = rotT(R, w);
     a = rotT(R, cross_add(a, al, t));
     al = rotT(R, al);
     g = rotT(R, g);
-    v = axpy(v, su, dql);
-    w = axpy(w, ss, dql);
-    const V3 xl = cross_add(cross(w, su), v, ss);
-    const V3 xa = cross(w, ss);
-    a = axpy(axpy(a, xl, dql), su, ddql);
-    al = axpy(axpy(al, xa, dql), ss, ddql);
+    if (REV)
+    {
+      w = axpy(w, ss, dql);
+      a = axpy(a, cross(v, ss), dql);
+      al = axpy(axpy(al, cross(w, ss), dql), ss, ddql);
+    }
+    else
+    {
+      v = axpy(v, su, dql);
+      w = axpy(w, ss, dql);
+      const V3 xl = cross_add(cross(w, su), v, ss);
+      const V3 xa = cross(w, ss);
+      a = axpy(axpy(a, xl, dql), su, ddql);
+      al = axpy(axpy(al, xa, dql), ss, ddql);
+    }
 #pragma unroll
     for (int j = 0; j < l; j++)
     {
@@ -185,9 +197,9 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GenIn
     for (int j = 0; j <= l; j++)
     {
       const V3 u = U[j], s = S[j];
-      const double e0 = dot(u, fm);
-      const V3 wu = cross(w, u);
-      const V3 h = cross_add(cross_add(cross(u, al), w, wu), fm, s);
+      const bool own = REV && j == l;  // u == 0 exactly
+      const double e0 = own ? 0.0 : dot(u, fm);
+      const V3 h = own ? cross(fm, s) : cross_add(cross_add(cross(u, al), w, cross(w, u)), fm, s);
       const V3 rho = cross(s, w);
       double e[10];
       e[0] = e0;
@@ -350,7 +362,7 @@ __device__ __forceinline__ void gram_mma_role(const SamplesDev& in, double* smem
   }
 }
 
-template <int NJ, int SLOTS>
+template <int NJ, int SLOTS, bool REV>
 __device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const SamplesDev& in, const double* __restrict__ tau_meas, double* smem,
                                               GramBars* bars, int s, int lane, int dbg)
 {
@@ -369,7 +381,7 @@ __device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const Sampl
     mbar_wait(&bars->empty[s], parity);  // consumers released the slot
     if (!(dbg & 1))
     {
-      gram_generate<NJ>(C, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
+      gram_generate<NJ, REV>(C, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
       if (i >= in.n) gram_zero_lane<NJ>(slot, lane);
     }
     __syncwarp();
@@ -377,7 +389,7 @@ __device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const Sampl
   }
 }
 
-template <int NJ, int SLOTS>
+template <int NJ, int SLOTS, bool REV>
 __global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
     gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const double* __restrict__ tau_meas, double* __restrict__ partial,
                       const int dbg)
@@ -399,7 +411,7 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
   // group of (iteration it, CTA, slot s): (it*gridDim.x + blockIdx.x)*SLOTS + s ; generator warp s fills slot s
   if (warp >= GF_MMA_WARPS)
   {
-    gram_gen_role<NJ, SLOTS>(C, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
+    gram_gen_role<NJ, SLOTS, REV>(C, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
     return;
   }
   // ------------------------------------------------ MMA warps: k-split index = warp % 4 (its SM sub-partition), tile-row parity = warp / 4
@@ -613,14 +625,14 @@ static ChainDev<NJ> narrow_g(const ChainDev<RDB_MAX_JOINTS>& h)
   return c;
 }
 
-template <int NJ, int SLOTS>
+template <int NJ, int SLOTS, bool REV>
 static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
                                    int accumulate, cudaStream_t st)
 {
   using G = GramGeom<NJ>;
   const size_t smem = sizeof(double) * (size_t)std::max(G::SLOT_DOUBLES * SLOTS, G::NT * 64);
   {
-    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   static const int dbg = [] { const char* e = getenv("RDB_GRAM_DEBUG"); return e ? atoi(e) : 0; }();  // 1: skip generation, 2: skip MMA (timing experiments only)
@@ -636,7 +648,7 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const do
     if (e != cudaSuccess) return e;
     ch.gram.fused_bytes = need;
   }
-  gram_fused_kernel<NJ, SLOTS><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), in, tau_meas, ch.gram.fused_partials, dbg);
+  gram_fused_kernel<NJ, SLOTS, REV><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), in, tau_meas, ch.gram.fused_partials, dbg);
   count_launch();
   if (ch.gram.fold_identity)
   {
@@ -671,10 +683,14 @@ cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double*
                               int accumulate, cudaStream_t st)
 {
   if (in.n <= 0 || ch.gram.fold_version != ch.model_version) return cudaErrorNotSupported;
+  bool rev = true;  // all moving joints revolute: the specialised generator
+  for (int j = 0; j < ch.gram.fold.nj; j++) rev = rev && ch.gram.fold.joint[j].type == RDB_JOINT_REVOLUTE;
   switch (ch.gram.fold.nj)  // moving joints; every joint of the folded chain is an input
   {
-#define X(N) \
-  case N: return launch_fused_nj<N, gf_slots<N>()>(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
+#define X(N)                                                                                                    \
+  case N:                                                                                                       \
+    return rev ? launch_fused_nj<N, gf_slots<N>(), true>(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st)  \
+               : launch_fused_nj<N, gf_slots<N>(), false>(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
     X(1) X(2) X(3) X(4) X(5) X(6) X(7)
 #undef X
   }

@@ -54,7 +54,9 @@ enum : int
 
 // Link-frame state of the walker after joint l: twist (v,w), acceleration (a,al) and gravity g of link l in link-l
 // axes at the link-l origin, and the unit twists (U[j],S[j]) of all joints j <= l at the same point/axes.
-template <int NJ_T, int MODE, class ChainT>
+// REV (unrolled torque / inertia kernels on the folded chain): every joint is revolute, so the joint type is a compile-time fact -- no type
+// selects and the linear half of the joint screws (an exact zero) is never multiplied
+template <int NJ_T, int MODE, bool REV = false, class ChainT>
 __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, double* __restrict__ phi, double* __restrict__ tau_out,
                                          double* __restrict__ M_out, int64_t ld_out, int64_t i)
 {
@@ -95,15 +97,22 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
     const JointDev& J = C.joint[l];
     double R[9];
     V3 t;
-    if (NJ_T > 0)
+    if (REV)
+    {
+      t = v3(J.t);
+      const double c1 = 1.0 - cv[NJ_T > 0 ? l : 0];
+#pragma unroll
+      for (int k = 0; k < 9; k++) R[k] = fma(c1, J.C[k], fma(sv[NJ_T > 0 ? l : 0], J.B[k], J.A[k]));
+    }
+    else if (NJ_T > 0)
       joint_transform_sc(J, qv[NJ_T > 0 ? l : 0], sv[NJ_T > 0 ? l : 0], cv[NJ_T > 0 ? l : 0], R, t);
     else
       joint_transform(J, ld_in(in.q, J.in, in.ld, i), R, t);
 
     // child-frame screw of joint l: [0;ax] revolute, [ax;0] prismatic, 0 fixed (R_pc^T axis_p == axis_j)
     const V3 axj = v3(J.ax);
-    const V3 su = (J.type == RDB_JOINT_PRISMATIC) ? axj : v3(0, 0, 0);
-    const V3 ss = (J.type == RDB_JOINT_REVOLUTE) ? axj : v3(0, 0, 0);
+    const V3 su = (!REV && J.type == RDB_JOINT_PRISMATIC) ? axj : v3(0, 0, 0);
+    const V3 ss = (REV || J.type == RDB_JOINT_REVOLUTE) ? axj : v3(0, 0, 0);
 
     if (kDyn)
     {
@@ -115,13 +124,22 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
       a = rotT(R, cross_add(a, al, t));
       al = rotT(R, al);
       g = rotT(R, g);
-      v = axpy(v, su, dql);
-      w = axpy(w, ss, dql);
-      // (v x s) Dq + s DDq, spatial cross of spacevect_algebra.h:88-93
-      const V3 xl = cross_add(cross(w, su), v, ss);
-      const V3 xa = cross(w, ss);
-      a = axpy(axpy(a, xl, dql), su, ddql);
-      al = axpy(axpy(al, xa, dql), ss, ddql);
+      if (REV)
+      {
+        w = axpy(w, ss, dql);
+        a = axpy(a, cross(v, ss), dql);
+        al = axpy(axpy(al, cross(w, ss), dql), ss, ddql);
+      }
+      else
+      {
+        v = axpy(v, su, dql);
+        w = axpy(w, ss, dql);
+        // (v x s) Dq + s DDq, spatial cross of spacevect_algebra.h:88-93
+        const V3 xl = cross_add(cross(w, su), v, ss);
+        const V3 xa = cross(w, ss);
+        a = axpy(axpy(a, xl, dql), su, ddql);
+        al = axpy(axpy(al, xa, dql), ss, ddql);
+      }
     }
 
     // unit twists of the joints already passed, moved to link l
@@ -227,7 +245,7 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
       const V3 f = cross_add(hl1, w, hl2);
       const V3 n = cross_add(cross_add(ha1, w, ha2), v, hl2);
 #pragma unroll
-      for (int j = 0; j <= l; j++) tau[j] += dot(U[j], f) + dot(S[j], n);
+      for (int j = 0; j <= l; j++) tau[j] += (REV && j == l) ? dot(S[j], n) : dot(U[j], f) + dot(S[j], n);
     }
 
     if (kInr)
@@ -238,12 +256,13 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
       for (int j = 0; j <= l; j++)
       {
         const V3 u = U[j], s = S[j];
-        const V3 hl = cross_add(u * P[0], s, mc);
+        const bool own = REV && j == l;  // u == 0 exactly
+        const V3 hl = own ? cross(s, mc) : cross_add(u * P[0], s, mc);
         const V3 Is = v3(fma(P[4], s.x, fma(P[5], s.y, P[6] * s.z)), fma(P[5], s.x, fma(P[7], s.y, P[8] * s.z)),
                          fma(P[6], s.x, fma(P[8], s.y, P[9] * s.z)));
-        const V3 ha = cross_add(Is, mc, u);
+        const V3 ha = own ? Is : cross_add(Is, mc, u);
 #pragma unroll
-        for (int k = 0; k <= j; k++) M[j * (j + 1) / 2 + k] += dot(U[k], hl) + dot(S[k], ha);
+        for (int k = 0; k <= j; k++) M[j * (j + 1) / 2 + k] += (own && k == j) ? dot(S[k], ha) : dot(U[k], hl) + dot(S[k], ha);
       }
     }
   }
@@ -275,13 +294,13 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
   }
 }
 
-template <int NJ, int MODE>
+template <int NJ, int MODE, bool REV = false>
 __global__ void __launch_bounds__(RDB_BLOCK, (MODE & DYN_REGRESSOR) ? RDB_REG_MINB : RDB_DYN_MINB) dyn_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, double* __restrict__ phi,
                                                         double* __restrict__ tau, double* __restrict__ M, int64_t ld_out)
 {
   const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
   if (i >= in.n) return;
-  dyn_body<NJ, MODE>(C, in, phi, tau, M, ld_out, i);
+  dyn_body<NJ, MODE, REV>(C, in, phi, tau, M, ld_out, i);
 }
 
 template <int MODE>
@@ -672,11 +691,16 @@ static cudaError_t launch_dyn_mode(const ChainHost& ch, const SamplesDev& in, do
   // never-moving joints folded away and the parameters lumped (gram_fused.cu: fold_chain) -- C6 walks 6 links instead of 7
   const bool folded = !(MODE & DYN_REGRESSOR) && ch.gram.fold_version == ch.model_version && ch.gram.fold.nj >= 1;
   const ChainDev<RDB_MAX_JOINTS>& H = folded ? ch.gram.fold : ch.host;
+  bool rev = folded;  // all-revolute specialisation (torque / inertia on the folded chain only)
+  for (int j = 0; j < H.nj && rev; j++) rev = H.joint[j].type == RDB_JOINT_REVOLUTE;
   switch (H.nj)
   {
-#define X(N)                                                                             \
-  case N:                                                                                \
-    dyn_kernel<N, MODE><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(H), in, phi, tau, M, ld_out); \
+#define X(N)                                                                                                                    \
+  case N:                                                                                                                       \
+    if ((MODE & DYN_REGRESSOR) == 0 && rev)                                                                                     \
+      dyn_kernel<N, (MODE & DYN_REGRESSOR) ? 0 : MODE, true><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(H), in, phi, tau, M, ld_out); \
+    else                                                                                                                        \
+      dyn_kernel<N, MODE><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(H), in, phi, tau, M, ld_out);                                   \
     break;
     RDB_FAST_NJ(X)
 #undef X
