@@ -326,6 +326,12 @@ __device__ __forceinline__ Tw transl(Tw t, V3 d) { return Tw{cross_add(t.l, t.a,
 // spatialCrossProduct, spacevect_algebra.h:88-93
 __device__ __forceinline__ Tw scross(Tw a, Tw b) { return Tw{cross_add(cross(a.a, b.l), a.l, b.a), cross(a.a, b.a)}; }
 __device__ __forceinline__ Tw tw_axpy(Tw y, Tw x, double s) { return Tw{axpy(y.l, x.l, s), axpy(y.a, x.a, s)}; }
+// y + x s where the linear half of x is a compile-time zero (ZL)
+template <bool ZL>
+__device__ __forceinline__ Tw tw_axpy_s(Tw y, Tw x, double s)
+{
+  return ZL ? Tw{y.l, axpy(y.a, x.a, s)} : Tw{axpy(y.l, x.l, s), axpy(y.a, x.a, s)};
+}
 __device__ __forceinline__ void st_tw(double* p, int link, int64_t ld, int64_t i, Tw t)
 {
   st3(p, (int64_t)6 * link, ld, i, t.l);
@@ -397,7 +403,8 @@ struct KinSm
   static constexpr size_t bytes = value ? sizeof(double) * 6 * NJ_T * RDB_BLOCK : 0;
 };
 
-template <int NJ_T, unsigned MASK, class ChainT>
+// NP (unrolled kernels): the chain has no prismatic joint, so the linear half of every base-frame screw is a compile-time zero
+template <int NJ_T, unsigned MASK, bool NP = false, class ChainT>
 __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, const KinOutDev& o, int64_t i, double* smp = nullptr)
 {
   constexpr int CAP = Cap<NJ_T>::value;
@@ -467,7 +474,7 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     // computeScrews (primitives_impl.h:879): screw of joint l in the base frame uses the PARENT link rotation
     const V3 axb = rot(R, v3(J.axp));
     Tw s;
-    s.l = (J.type == RDB_JOINT_PRISMATIC) ? axb : v3(0, 0, 0);
+    s.l = (!NP && J.type == RDB_JOINT_PRISMATIC) ? axb : v3(0, 0, 0);
     s.a = (J.type == RDB_JOINT_REVOLUTE) ? axb : v3(0, 0, 0);
 
     // computeFrames (primitives_impl.h:869)
@@ -508,13 +515,13 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     Tw vxs = tw0();
     if (cVel)
     {
-      v = tw_axpy(transl(v, d), s, dql);  // primitives_impl.h:1007-1008
-      vxs = scross(v, s);
+      v = tw_axpy_s<NP>(transl(v, d), s, dql);  // primitives_impl.h:1007-1008
+      vxs = NP ? Tw{cross(v.l, s.a), cross(v.a, s.a)} : scross(v, s);
       if (wV) st_tw(o.twist, l + 1, ld, i, v);
     }
     if (MASK & K_DTWIST_LIN)
     {
-      al = tw_axpy(transl(al, d), s, ddql);  // primitives_impl.h:1055-1056
+      al = tw_axpy_s<NP>(transl(al, d), s, ddql);  // primitives_impl.h:1055-1056
       if (wAl) st_tw(o.dtwist_lin, l + 1, ld, i, al);
     }
     if (MASK & K_DTWIST_NONLIN)
@@ -524,23 +531,23 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     }
     if (cAcc)
     {
-      a = tw_axpy(tw_axpy(transl(a, d), vxs, dql), s, ddql);  // primitives_impl.h:1116-1117
+      a = tw_axpy_s<NP>(tw_axpy(transl(a, d), vxs, dql), s, ddql);  // primitives_impl.h:1116-1117
       if (wA) st_tw(o.dtwist, l + 1, ld, i, a);
     }
     if (MASK & K_DDTWIST_LIN)
     {
-      jl = tw_axpy(transl(jl, d), s, dddql);  // primitives_impl.h:1148-1149
+      jl = tw_axpy_s<NP>(transl(jl, d), s, dddql);  // primitives_impl.h:1148-1149
       if (wJl) st_tw(o.ddtwist_lin, l + 1, ld, i, jl);
     }
     if (cJer)
     {
       // primitives_impl.h:1213-1218 / 1174-1178; the reference's 1x coefficient on (v x s) DDq is mirrored
-      const Tw axs = scross(a, s);
+      const Tw axs = NP ? Tw{cross(a.l, s.a), cross(a.a, s.a)} : scross(a, s);
       const Tw vvxs = scross(v, vxs);
       const Tw k = Tw{axs.l + vvxs.l, axs.a + vvxs.a};
       if (MASK & K_DDTWIST)
       {
-        jf = tw_axpy(tw_axpy(tw_axpy(transl(jf, d), s, dddql), vxs, ddql), k, dql);
+        jf = tw_axpy(tw_axpy(tw_axpy_s<NP>(transl(jf, d), s, dddql), vxs, ddql), k, dql);
         if (wJ) st_tw(o.ddtwist, l + 1, ld, i, jf);
       }
       if (MASK & K_DDTWIST_NONLIN)
@@ -577,7 +584,7 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
         // s_j . dualTransl(w, p_j - p): the force part for a prismatic joint, the moment about the joint origin for a revolute one
         const int tj = C.joint[j].type;
         if (tj == RDB_JOINT_REVOLUTE) tau[j] += dot(js.ab(j), cross_add(n, f, js.pj(j) - p));
-        else if (tj == RDB_JOINT_PRISMATIC) tau[j] += dot(js.ab(j), f);
+        else if (!NP && tj == RDB_JOINT_PRISMATIC) tau[j] += dot(js.ab(j), f);
       }
     }
   }
@@ -596,7 +603,7 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
         const int tj = C.joint[j].type;
         const V3 z = v3(0, 0, 0);
         const V3 abj = js.ab(j);
-        const V3 lin = tj == RDB_JOINT_REVOLUTE ? cross(abj, p - js.pj(j)) : (tj == RDB_JOINT_PRISMATIC ? abj : z);
+        const V3 lin = tj == RDB_JOINT_REVOLUTE ? cross(abj, p - js.pj(j)) : ((!NP && tj == RDB_JOINT_PRISMATIC) ? abj : z);
         st3(o.jacobian, (int64_t)6 * r, ld, i, lin);
         st3(o.jacobian, (int64_t)6 * r + 3, ld, i, tj == RDB_JOINT_REVOLUTE ? abj : z);
       }
@@ -614,13 +621,13 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
   (void)n_in;
 }
 
-template <int NJ, unsigned MASK>
+template <int NJ, unsigned MASK, bool NP = false>
 __global__ void __launch_bounds__(RDB_BLOCK, RDB_KIN_MINB) kin_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const KinOutDev o)
 {
   extern __shared__ double kin_sm[];
   const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
   if (i >= in.n) return;
-  kin_body<NJ, MASK>(C, in, o, i, kin_sm + threadIdx.x);
+  kin_body<NJ, MASK, NP>(C, in, o, i, kin_sm + threadIdx.x);
 }
 
 template <unsigned MASK>
@@ -729,11 +736,14 @@ static cudaError_t launch_kin_mask(const ChainHost& ch, const SamplesDev& in, co
 {
   if (in.n <= 0) return cudaSuccess;
   const unsigned grid = grid_for(in.n);
+  bool np = true;  // no prismatic joint: the specialised kernels
+  for (int j = 0; j < ch.host.nj; j++) np = np && ch.host.joint[j].type != RDB_JOINT_PRISMATIC;
   switch (ch.host.nj)
   {
-#define X(N)                                                                   \
-  case N:                                                                      \
-    kin_kernel<N, MASK><<<grid, RDB_BLOCK, KinSm<N, MASK>::bytes, st>>>(narrow<N>(ch.host), in, o); \
+#define X(N)                                                                                                        \
+  case N:                                                                                                           \
+    if (np) kin_kernel<N, MASK, true><<<grid, RDB_BLOCK, KinSm<N, MASK>::bytes, st>>>(narrow<N>(ch.host), in, o);   \
+    else kin_kernel<N, MASK, false><<<grid, RDB_BLOCK, KinSm<N, MASK>::bytes, st>>>(narrow<N>(ch.host), in, o);     \
     break;
     RDB_FAST_NJ(X)
 #undef X
