@@ -192,6 +192,19 @@ rdb_status rdb_wrench_batch(const rdb_chain* chain, const rdb_samples* in, const
 rdb_status rdb_jacobian_link_batch(const rdb_chain* chain, const rdb_samples* in, int32_t link_index, double* jacobian, int64_t ld_out,
                                    void* stream);
 
+/* Chain::computeLocalIk / computeWeigthedLocalIk (PI.h:1398-1468), batched: for every target pose, Gauss-Newton steps
+ *   dq = argmin |J dq - e|^2_W  s.t.  q_min <= sol + dq <= q_max,   e = getFrameDistance(T_target, T(sol))  (frame_distance.h:44-49)
+ * from `seed` until |W e| < toll.  The reference's wall-clock budget (ros::Duration max_time) becomes an ITERATION budget `max_iter`
+ * (at most max_iter steps, max_iter + 1 convergence checks) and Eigen::solve_quadprog of the un-vendored eigen_matrix_utils becomes an exact
+ * box-constrained active-set solve.  target[12][ld]: 3x4 [R|p] row-major planes (the layout of rdb_kinematics_out.T_tool);
+ * seed / sol [n_inputs][ld]; q_min / q_max [n_inputs] HOST arrays (NULL = -/+1e10, the reference's no-limit default, PI.h:92-93);
+ * weight[6] host array or NULL (NULL = computeLocalIk).  Optional outputs: status[n] (1 = converged, the reference's return value),
+ * iterations[n], error_norm[n] (|W e| at return).  n_inputs <= RDB_IK_MAX_INPUTS. */
+#define RDB_IK_MAX_INPUTS 8
+rdb_status rdb_local_ik_batch(const rdb_chain* chain, int64_t n, int64_t ld, const double* target, const double* seed, const double* q_min,
+                              const double* q_max, const double* weight, double toll, int32_t max_iter, double* sol, int32_t* status,
+                              int32_t* iterations, double* error_norm, void* stream);
+
 /* ---- additive joint components ------------------------------------------------------------
  * The reference models joint friction / elasticity as per-joint "components" whose regressor columns are appended to the
  * inertial regressor by the identification code (base_component.h:124-139).  Column blocks, in the order given here:

@@ -197,6 +197,15 @@ public:
     if (s == RDB_ERR_NOT_FOUND) throw std::invalid_argument(rdb_last_error());
     check(s);
   }
+  // Chain::computeLocalIk / computeWeigthedLocalIk (primitives_impl.h:1398-1468) for n target poses (device planes: target[12][ld] 3x4
+  // row-major, seed / sol [n_act][ld]); the wall-clock budget of the reference is an iteration budget.  q_min / q_max / weight: host
+  // arrays or nullptr (no limits / unweighted).  status[i] = 1 where the reference would return true.
+  void computeLocalIk(int64_t n, int64_t ld, const double* target, const double* seed, const double* q_min, const double* q_max,
+                      const double* weight, double toll, int32_t max_iter, double* sol, int32_t* status = nullptr,
+                      int32_t* iterations = nullptr, double* error_norm = nullptr, void* stream = nullptr)
+  {
+    check(rdb_local_ik_batch(m_h, n, ld, target, seed, q_min, q_max, weight, toll, max_iter, sol, status, iterations, error_norm, stream));
+  }
   // additive joint components (friction_polynomial1.h, friction_polynomial2.h, ideal_spring.h) as extra regressor columns
   unsigned int setComponents(const std::vector<rdb_component_desc>& components)
   {

@@ -196,6 +196,22 @@ class OracleChain:
         f(self._h, n, n, _ptr(q), int(link), n, _ptr(J))
         return J
 
+    def local_ik(self, target, seed, q_min=None, q_max=None, weight=None, toll=1e-6, max_iter=50):
+        """computeLocalIk / computeWeigthedLocalIk (PI.h:1398-1468) with an iteration budget: (sol[n_in][N], status[N], iters[N], err[N])."""
+        target, seed = _c(target, 12), _c(seed, self.n_in)
+        n = target.shape[1]
+        qmin = None if q_min is None else np.ascontiguousarray(q_min, dtype=np.float64)
+        qmax = None if q_max is None else np.ascontiguousarray(q_max, dtype=np.float64)
+        w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+        sol, err = np.zeros((self.n_in, n)), np.zeros(n)
+        status, iters = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        f = self._l.lib.oracle_local_ik_batch
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64] + [_dbl_p] * 5 + [ctypes.c_double, ctypes.c_int, _dbl_p, i32p, i32p, _dbl_p]
+        f(self._h, n, n, _ptr(target), _ptr(seed), _ptr(qmin), _ptr(qmax), _ptr(w), float(toll), int(max_iter), _ptr(sol),
+          status.ctypes.data_as(i32p), iters.ctypes.data_as(i32p), _ptr(err))
+        return sol, status, iters, err
+
     def gram(self, q, dq, ddq, tau_meas=None):
         q, dq, ddq, tau_meas = (_c(x, self.n_in) for x in (q, dq, ddq, tau_meas))
         n = q.shape[1]

@@ -670,6 +670,217 @@ void oracle_eval(const oracle_chain* c, const double* q, const double* dq, const
 }
 
 /* ------------------------------------------------------------------ batched drivers (SoA planes, like the ABI) */
+/* ------------------------------------------------------------------ local IK (PI.h:1398-1468, frame_distance.h:44-49) */
+/* Eigen::AngleAxisd(Matrix3d) = AngleAxis(Quaternion(m)); returns angle * axis (m row-major).
+ * Quaternion from matrix: Eigen/src/Geometry/Quaternion.h (quaternionbase_assign_impl<Other,3,3>); angle-axis from quaternion:
+ * Eigen/src/Geometry/AngleAxis.h (operator=(QuaternionBase)).  Eigen is un-vendored by the reference; published algorithm restated. */
+static void angle_axis_of_matrix(const double* m, double* out)
+{
+  double q[4]; /* x y z w */
+  double t = m[0] + m[4] + m[8];
+  if (t > 0.0)
+  {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (m[7] - m[5]) * t;
+    q[1] = (m[2] - m[6]) * t;
+    q[2] = (m[3] - m[1]) * t;
+  }
+  else
+  {
+    int i = 0;
+    if (m[4] > m[0]) i = 1;
+    if (m[8] > m[4 * i]) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(m[4 * i] - m[4 * j] - m[4 * k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (m[3 * k + j] - m[3 * j + k]) * t;
+    q[j] = (m[3 * j + i] + m[3 * i + j]) * t;
+    q[k] = (m[3 * k + i] + m[3 * i + k]) * t;
+  }
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  if (n != 0.0)
+  {
+    double angle = 2.0 * atan2(n, fabs(q[3]));
+    if (q[3] < 0.0) n = -n;
+    for (int c = 0; c < 3; c++) out[c] = angle * (q[c] / n);
+  }
+  else
+    out[0] = out[1] = out[2] = 0.0;
+}
+
+/* getFrameDistance(T_wa, T_wb) with T = [R | p] 3x4 row-major (frame_distance.h:44-49) */
+void oracle_frame_distance(const double* Ta, const double* Tb, double* d)
+{
+  double Ra[9], Rb[9], Rab[9], aa[3];
+  for (int r = 0; r < 3; r++)
+    for (int k = 0; k < 3; k++)
+    {
+      Ra[3 * r + k] = Ta[4 * r + k];
+      Rb[3 * r + k] = Tb[4 * r + k];
+    }
+  for (int r = 0; r < 3; r++) d[r] = Ta[4 * r + 3] - Tb[4 * r + 3];
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) Rab[3 * a + b] = Ra[a] * Rb[b] + Ra[3 + a] * Rb[3 + b] + Ra[6 + a] * Rb[6 + b]; /* R_a^-1 R_b */
+  angle_axis_of_matrix(Rab, aa);
+  for (int a = 0; a < 3; a++) d[3 + a] = -(Ra[3 * a] * aa[0] + Ra[3 * a + 1] * aa[1] + Ra[3 * a + 2] * aa[2]);
+}
+
+/* The QP of PI.h:1421-1427: min 1/2 x^T H x + f^T x s.t. lo <= x <= hi (CI = [I, -I], ci0 = [sol - q_min; q_max - sol], no equalities).
+ * Eigen::solve_quadprog lives in the un-vendored eigen_matrix_utils (rosdyn.rosinstall:7-9); what it returns is the minimiser, which a
+ * primal active-set method finds as well.  Directions in which H is numerically singular are left where they are. */
+#define OR_IK_MAXN 8
+void oracle_box_qp(int n, const double* H, const double* f, const double* lo, const double* hi, double* x)
+{
+  int state[OR_IK_MAXN]; /* 0 free, 1 at lo, 2 at hi, 3 pinned */
+  double hmx = 0.0, fmx = 0.0;
+  for (int i = 0; i < n; i++)
+  {
+    hmx = fmax(hmx, H[i * n + i]);
+    fmx = fmax(fmx, fabs(f[i]));
+    x[i] = 0.0;
+    state[i] = 0;
+    if (lo[i] >= hi[i]) { x[i] = lo[i]; state[i] = 3; }
+    else if (x[i] <= lo[i]) { x[i] = lo[i]; state[i] = 1; }
+    else if (x[i] >= hi[i]) { x[i] = hi[i]; state[i] = 2; }
+  }
+  const double ptol = 1e-13 * hmx, gtol = 1e-12 * (fmx + hmx);
+  for (int it = 0; it < 6 * OR_IK_MAXN + 8; it++)
+  {
+    double g[OR_IK_MAXN], d[OR_IK_MAXN], L[OR_IK_MAXN][OR_IK_MAXN], y[OR_IK_MAXN];
+    int idx[OR_IK_MAXN], ok[OR_IK_MAXN], m = 0;
+    for (int i = 0; i < n; i++)
+    {
+      double s = f[i];
+      for (int k = 0; k < n; k++) s += H[i * n + k] * x[k];
+      g[i] = s;
+      d[i] = 0.0;
+      if (state[i] == 0) idx[m++] = i;
+    }
+    for (int a = 0; a < m; a++)
+      for (int b = 0; b <= a; b++)
+      {
+        double s = H[idx[a] * n + idx[b]];
+        for (int k = 0; k < b; k++) s -= L[a][k] * L[b][k];
+        if (a == b)
+        {
+          ok[a] = s > ptol;
+          L[a][a] = ok[a] ? sqrt(s) : 1.0;
+          if (!ok[a])
+            for (int k = 0; k < a; k++) L[a][k] = 0.0;
+        }
+        else
+          L[a][b] = ok[b] ? s / L[b][b] : 0.0;
+      }
+    for (int a = 0; a < m; a++)
+    {
+      double s = ok[a] ? -g[idx[a]] : 0.0;
+      for (int k = 0; k < a; k++) s -= L[a][k] * y[k];
+      y[a] = s / L[a][a];
+    }
+    for (int a = m - 1; a >= 0; a--)
+    {
+      double s = y[a];
+      for (int k = a + 1; k < m; k++) s -= L[k][a] * d[idx[k]];
+      d[idx[a]] = ok[a] ? s / L[a][a] : 0.0;
+    }
+    double alpha = 1.0;
+    int blocking = -1, bstate = 0;
+    for (int a = 0; a < m; a++)
+    {
+      int i = idx[a];
+      if (d[i] > 0.0 && x[i] + d[i] > hi[i])
+      {
+        double s = (hi[i] - x[i]) / d[i];
+        if (s < alpha) { alpha = s; blocking = i; bstate = 2; }
+      }
+      else if (d[i] < 0.0 && x[i] + d[i] < lo[i])
+      {
+        double s = (lo[i] - x[i]) / d[i];
+        if (s < alpha) { alpha = s; blocking = i; bstate = 1; }
+      }
+    }
+    for (int a = 0; a < m; a++) x[idx[a]] += alpha * d[idx[a]];
+    if (blocking >= 0)
+    {
+      x[blocking] = bstate == 1 ? lo[blocking] : hi[blocking];
+      state[blocking] = bstate;
+      continue;
+    }
+    int worst = -1;
+    double wv = gtol;
+    for (int i = 0; i < n; i++)
+    {
+      if (state[i] != 1 && state[i] != 2) continue;
+      double s = f[i];
+      for (int k = 0; k < n; k++) s += H[i * n + k] * x[k];
+      double viol = state[i] == 1 ? -s : s;
+      if (viol > wv) { wv = viol; worst = i; }
+    }
+    if (worst < 0) break;
+    state[worst] = 0;
+  }
+}
+
+/* computeLocalIk (weight == NULL, PI.h:1398-1432) / computeWeigthedLocalIk (PI.h:1435-1468) for n targets.  The reference's wall-clock
+ * budget is an iteration budget here: at most max_iter steps, max_iter + 1 convergence checks.  target[12][ld] (3x4 row-major planes),
+ * seed / sol [n_in][ld]; status 1 = converged (the reference's return value). */
+void oracle_local_ik_batch(const oracle_chain* c, int64_t n, int64_t ld, const double* target, const double* seed, const double* q_min,
+                           const double* q_max, const double* weight, double toll, int max_iter, double* sol_out, int32_t* status,
+                           int32_t* iters, double* err_norm)
+{
+  const int n_in = c->n_in, nL = c->nL;
+  if (n_in > OR_IK_MAXN) return;
+  for (int64_t i = 0; i < n; i++)
+  {
+    double Ta[12], sol[OR_IK_MAXN], bT[OR_MAXL * 12], J[OR_IK_MAXN * 6], e[6], en = 0.0;
+    for (int k = 0; k < 12; k++) Ta[k] = target[(int64_t)k * ld + i];
+    for (int r = 0; r < n_in; r++) sol[r] = seed[(int64_t)r * ld + i];
+    int done = 0, it = 0;
+    for (;; it++)
+    {
+      oracle_out o;
+      memset(&o, 0, sizeof(o));
+      o.T_links = bT;
+      o.jacobian = J;
+      oracle_eval(c, sol, NULL, NULL, NULL, &o);
+      oracle_frame_distance(Ta, bT + 12 * (nL - 1), e);
+      en = 0.0;
+      for (int k = 0; k < 6; k++)
+      {
+        double we = weight ? weight[k] * e[k] : e[k];
+        en += we * we;
+      }
+      en = sqrt(en);
+      if (en < toll) { done = 1; break; }
+      if (it >= max_iter) break;
+      double H[OR_IK_MAXN * OR_IK_MAXN], f[OR_IK_MAXN], lo[OR_IK_MAXN], hi[OR_IK_MAXN], dq[OR_IK_MAXN];
+      for (int a = 0; a < n_in; a++)
+      {
+        for (int b = 0; b < n_in; b++)
+        {
+          double s = 0.0;
+          for (int k = 0; k < 6; k++) s += J[6 * a + k] * (weight ? weight[k] : 1.0) * J[6 * b + k];
+          H[a * n_in + b] = s;
+        }
+        double s = 0.0;
+        for (int k = 0; k < 6; k++) s += J[6 * a + k] * (weight ? weight[k] : 1.0) * e[k];
+        f[a] = -s;
+        lo[a] = (q_min ? q_min[a] : -1e10) - sol[a];
+        hi[a] = (q_max ? q_max[a] : 1e10) - sol[a];
+      }
+      oracle_box_qp(n_in, H, f, lo, hi, dq);
+      for (int a = 0; a < n_in; a++) sol[a] += dq[a];
+    }
+    for (int r = 0; r < n_in; r++) sol_out[(int64_t)r * ld + i] = sol[r];
+    if (status) status[i] = done;
+    if (iters) iters[i] = it;
+    if (err_norm) err_norm[i] = en;
+  }
+}
+
 static int or_threads(int nthreads)
 {
 #ifdef _OPENMP

@@ -61,6 +61,9 @@ SYMBOLS = {
     "rdb_regressor_gram_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, _dp, _dp, i32, ctypes.c_void_p]),
     "rdb_wrench_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, _dp, _dp, i64, ctypes.c_void_p]),
     "rdb_jacobian_link_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), i32, _dp, i64, ctypes.c_void_p]),
+    "rdb_local_ik_batch": (i32, [ctypes.c_void_p, i64, i64, _dp, _dp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                 ctypes.POINTER(ctypes.c_double), ctypes.c_double, i32, _dp, ctypes.c_void_p, ctypes.c_void_p, _dp,
+                                 ctypes.c_void_p]),
     "rdb_component_columns": (i32, [i32]),
     "rdb_chain_set_components": (i32, [ctypes.c_void_p, i32, ctypes.POINTER(CComponentDesc)]),
     "rdb_chain_component_columns": (i32, [ctypes.c_void_p]),

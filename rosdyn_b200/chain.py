@@ -286,6 +286,45 @@ class Chain:
         r = _swap01(J.reshape(self.n_in, 6, n))
         return r[..., 0] if single else r
 
+    def computeLocalIk(self, T_b_t, seed, q_min=None, q_max=None, weight=None, toll: float = 1e-6, max_iter: int = 50):
+        """Chain::computeLocalIk / computeWeigthedLocalIk (PI.h:1398-1468), batched over N target poses.
+        T_b_t: 12 planes (3x4 [R|p] row-major, as kinematics(...)["T_tool"] returns them) x N, or one 4x4 / 3x4 pose; seed: n_act (x N).
+        The reference's wall-clock budget is an iteration budget (max_iter).  Returns (sol, converged, iterations, error_norm).
+        Device (torch CUDA) arrays only; q_min / q_max / weight are small host arrays (None = no limits / unweighted)."""
+        if not _is_torch(T_b_t) or not T_b_t.is_cuda:
+            raise ValueError("computeLocalIk takes device (torch CUDA) arrays")
+        single = seed.dim() == 1
+        T = T_b_t.to(torch.float64)
+        if single:
+            T = T[:3, :].reshape(12, 1)
+        T = T.reshape(12, -1).contiguous()
+        sd = seed.to(torch.float64).reshape(self.n_in, -1).contiguous()
+        n = T.shape[1]
+        if sd.shape[1] != n:
+            raise ValueError("Input data dimensions mismatch")
+
+        def host(a, m):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (m,):
+                raise ValueError("Input data dimensions mismatch")
+            return a
+        qmin, qmax, w = host(q_min, self.n_in), host(q_max, self.n_in), host(weight, 6)
+        dp = ctypes.POINTER(ctypes.c_double)
+        hp = lambda a: None if a is None else a.ctypes.data_as(dp)  # noqa: E731
+        sol = torch.empty((self.n_in, max(n, 1)), dtype=torch.float64, device=T.device)[:, :n]
+        stat = torch.zeros((max(n, 1),), dtype=torch.int32, device=T.device)[:n]
+        its = torch.zeros((max(n, 1),), dtype=torch.int32, device=T.device)[:n]
+        err = torch.zeros((max(n, 1),), dtype=torch.float64, device=T.device)[:n]
+        check(self._lib.rdb_local_ik_batch(self._h, n, max(n, 1), _ptr(T), _ptr(sd), hp(qmin), hp(qmax), hp(w), float(toll), int(max_iter),
+                                           _ptr(sol), _ptr(stat), _ptr(its), _ptr(err), self._stream()))
+        if single:
+            return sol[:, 0], bool(stat[0].item()), int(its[0].item()), float(err[0].item())
+        return sol, stat, its, err
+
+    computeWeigthedLocalIk = computeLocalIk  # the reference's spelling (PI.h:1435); pass weight=
+
     def getTransformationLink(self, q, link_name):
         """Chain::getTransformationLink (PI.h:912-925)."""
         names = self.getLinksName()

@@ -385,6 +385,21 @@ rdb_status rdb_jacobian_link_batch(const rdb_chain* chain, const rdb_samples* in
   return RDB_OK;
 }
 
+rdb_status rdb_local_ik_batch(const rdb_chain* chain, int64_t n, int64_t ld, const double* target, const double* seed, const double* q_min,
+                              const double* q_max, const double* weight, double toll, int32_t max_iter, double* sol, int32_t* status,
+                              int32_t* iterations, double* error_norm, void* stream)
+{
+  if (!chain) return fail(RDB_ERR_INVALID_ARG, "null chain");
+  if (n < 0 || ld < n) return fail(RDB_ERR_INVALID_ARG, "need 0 <= n <= ld");
+  if (chain->host.n_in > RDB_IK_MAX_INPUTS) return fail(RDB_ERR_INVALID_ARG, "local IK supports at most RDB_IK_MAX_INPUTS input joints");
+  if (n == 0) return RDB_OK;
+  if (!target || !sol || (!seed && chain->host.n_in > 0)) return fail(RDB_ERR_INVALID_ARG, "target, seed and sol are required");
+  if (max_iter < 0 || !(toll >= 0.0)) return fail(RDB_ERR_INVALID_ARG, "max_iter and toll must be non-negative");
+  RDB_CUDA(launch_ik(*chain, n, ld, target, seed, q_min, q_max, weight, toll, max_iter, sol, status, iterations, error_norm,
+                     (cudaStream_t)stream));
+  return RDB_OK;
+}
+
 // ------------------------------------------------------------------------------------------- components (N2)
 int32_t rdb_component_columns(int32_t type)
 {

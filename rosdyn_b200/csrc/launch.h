@@ -82,6 +82,10 @@ cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_m
 // aux.cu: getWrench / getJointTorque with external wrenches, getJacobianLink (two-pass kernels, not the throughput path)
 cudaError_t launch_aux(const ChainHost& ch, const SamplesDev& in, const double* ext, int64_t ld_ext, double* torque, double* wrenches,
                        double* jac_link, int link, int64_t ld_out, cudaStream_t st);
+// ik.cu: batched local IK (Chain::computeLocalIk, primitives_impl.h:1398-1468)
+cudaError_t launch_ik(const ChainHost& ch, int64_t n, int64_t ld, const double* target, const double* seed, const double* q_min,
+                      const double* q_max, const double* weight, double tol, int max_iter, double* sol, int32_t* status, int32_t* iters,
+                      double* err, cudaStream_t st);
 // components.cu
 cudaError_t launch_components_regressor(const ChainHost& ch, const SamplesDev& in, double* phi_c, int64_t ld_out, cudaStream_t st);
 cudaError_t launch_components_torque(const ChainHost& ch, const SamplesDev& in, const ComponentParams& prm, double* torque, int64_t ld_out,
