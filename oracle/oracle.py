@@ -20,7 +20,8 @@ def build(force: bool = False) -> None:
     """Compile the C restatement (gcc); a no-op when the .so is newer than the source."""
     so = os.path.join(_HERE, "librosdyn_oracle.so")
     src = os.path.join(_HERE, "rosdyn_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [src, os.path.join(_HERE, "box_qp.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "all"])
 
 
@@ -38,7 +39,8 @@ def build_ref(force: bool = False) -> bool:
     the prebuilt file)."""
     if not os.path.isdir(REFERENCE_ROOT):
         return os.path.exists(REF_LIB)
-    deps = [os.path.join(_HERE, "ref_driver.cpp"), os.path.join(_HERE, "shim", "mini_eigen.h")]
+    deps = [os.path.join(_HERE, "ref_driver.cpp"), os.path.join(_HERE, "shim", "mini_eigen.h"), os.path.join(_HERE, "box_qp.h"),
+            os.path.join(_HERE, "shim", "ros", "ros.h"), os.path.join(_HERE, "shim", "eigen_matrix_utils", "eiquadprog.hpp")]
     if force or not os.path.exists(REF_LIB) or any(os.path.getmtime(REF_LIB) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
     return True

@@ -15,6 +15,7 @@
 #include <omp.h>
 #endif
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -29,6 +30,10 @@ struct RefChain
   std::shared_ptr<urdf::Model> model;
   rosdyn::ChainPtr chain;
   std::vector<std::string> input_names;
+  std::vector<std::shared_ptr<urdf::Joint>> ujoints;  // by chain joint (limits are re-read by createChain)
+  std::vector<int> input_of_joint;
+  Eigen::Vector3d gravity;
+  std::string base_name, tool_name;
   std::vector<rosdyn::ChainPtr> per_thread;  // rosdyn::Chain is stateful and not reentrant: one clone() per worker (primitives.h:554)
   int nJ = 0, nL = 0, n_in = 0;
   // chains for `nthreads` workers (0 = all); worker 0 uses the original
@@ -191,10 +196,15 @@ void* oracle_chain_create(const rdb_chain_desc* d)
       links[j]->child_links.push_back(links[j + 1]);
       links[j + 1]->parent_joint = uj;
       if (J.input_index >= 0 && J.input_index < rc->n_in) input_names[J.input_index] = uj->name;
+      rc->ujoints.push_back(uj);
+      rc->input_of_joint.push_back(J.input_index);
     }
     rc->model->root_link_ = links[0];
     Eigen::Vector3d g;
     g << d->gravity[0], d->gravity[1], d->gravity[2];
+    rc->gravity = g;
+    rc->base_name = links.front()->name;
+    rc->tool_name = links.back()->name;
     rc->chain = rosdyn::createChain(*rc->model, links.front()->name, links.back()->name, g);
     if (!rc->chain) return nullptr;
     rc->chain->setInputJointsName(input_names);
@@ -338,6 +348,59 @@ void oracle_jacobian_link_batch(const void* cv, int64_t n, int64_t ld, const dou
 }
 
 // normal equations of the reference's regressor / torque with long-double accumulation
+// Chain::computeLocalIk / computeWeigthedLocalIk of the reference (primitives_impl.h:1398-1468) for n targets.  The joint limits go in
+// through the urdf model (Joint::fromUrdf reads them, Chain::setInputJointsName copies them to m_q_min / m_q_max); the wall clock is the
+// shim's tick clock, so that `max_iter + 1` loop iterations run (the restatement allows max_iter steps and max_iter + 1 checks; the
+// reference checks at the top of each iteration only); solve_quadprog is the stand-in of shim/eigen_matrix_utils.
+void oracle_local_ik_batch(void* cv, int64_t n, int64_t ld, const double* target, const double* seed, const double* q_min, const double* q_max,
+                           const double* weight, double toll, int max_iter, double* sol_out, int32_t* status, int32_t* iters, double* err_norm)
+{
+  RefChain* rc = static_cast<RefChain*>(cv);
+  try
+  {
+  for (size_t j = 0; j < rc->ujoints.size(); j++)
+  {
+    const int r = rc->input_of_joint[j];
+    if (r < 0 || r >= rc->n_in) continue;
+    rc->ujoints[j]->limits->lower = q_min ? q_min[r] : -1e10;
+    rc->ujoints[j]->limits->upper = q_max ? q_max[r] : 1e10;
+  }
+  rosdyn::ChainPtr ch = rosdyn::createChain(*rc->model, rc->base_name, rc->tool_name, rc->gravity);
+  ch->setInputJointsName(rc->input_names);
+  const int n_in = rc->n_in;
+  for (int64_t i = 0; i < n; i++)
+  {
+    Eigen::Affine3d T;
+    for (int r = 0; r < 3; r++)
+      for (int k = 0; k < 4; k++) T.matrix()(r, k) = target[(int64_t)(4 * r + k) * ld + i];
+    Eigen::VectorXd sd(n_in), sol(n_in);
+    for (int r = 0; r < n_in; r++) sd(r) = seed[(int64_t)r * ld + i];
+    ros::Time::ticks() = 0;
+    bool ok;
+    if (weight)
+    {
+      Eigen::Vector6d w;
+      for (int k = 0; k < 6; k++) w(k) = weight[k];
+      ok = ch->computeWeigthedLocalIk(sol, T, w, sd, toll, ros::Duration(max_iter + 1.5));
+    }
+    else
+      ok = ch->computeLocalIk(sol, T, sd, toll, ros::Duration(max_iter + 1.5));
+    const long used = ros::Time::ticks();  // 1 (tini) + one per loop test
+    ros::Time::ticks() = -1;
+    for (int r = 0; r < n_in; r++) sol_out[(int64_t)r * ld + i] = sol(r);
+    if (status) status[i] = ok ? 1 : 0;
+    if (iters) iters[i] = (int32_t)(used - 2);  // steps taken before the successful check
+    if (err_norm) err_norm[i] = 0.0;
+  }
+  }
+  catch (const std::exception& e)
+  {
+    fprintf(stderr, "oracle_local_ik_batch (reference build): %s\n", e.what());
+    if (status)
+      for (int64_t i = 0; i < n; i++) status[i] = -1;
+  }
+}
+
 void oracle_regressor_gram(const void* cv, int64_t n, int64_t ld, const double* q, const double* dq, const double* ddq, const double* tau_meas,
                            double* gram, double* rhs, double* tau_sq)
 {

@@ -108,10 +108,19 @@ class Time
 {
 public:
   double s = 0;
+  // >= 0: deterministic clock for the checker, one second per call (turns the wall-clock budget of Chain::computeLocalIk,
+  // primitives_impl.h:1405, into an iteration budget); < 0: the steady clock
+  static long& ticks()
+  {
+    static thread_local long t = -1;
+    return t;
+  }
   static Time now()
   {
     Time t;
-    t.s = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    long& k = ticks();
+    if (k >= 0) t.s = (double)(k++);
+    else t.s = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     return t;
   }
   Duration operator-(const Time& o) const { return Duration(s - o.s); }

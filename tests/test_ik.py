@@ -2,8 +2,9 @@
 
 CPU: the oracle's box-QP against brute-force enumeration of the active sets, its frame distance against an independent numpy formula,
 its IK loop through the properties the problem defines (converged poses reproduce the target, limits hold).
-GPU: rdb_local_ik_batch against the oracle on the same targets / seeds.  The reference's QP solver (eigen_matrix_utils) is un-vendored and
-its loop runs on a wall-clock budget, so this row is pinned by those properties, not by reference outputs (parity unpinned for IK)."""
+      and against the reference's OWN loop run in oracle/_ref (tick clock for the wall-clock budget, stand-in box-QP for the un-vendored
+      solve_quadprog of eigen_matrix_utils -- the one piece of this row no reference output can pin).
+GPU: rdb_local_ik_batch against the oracle on the same targets / seeds."""
 import ctypes
 import itertools
 
@@ -129,6 +130,30 @@ def test_oracle_ik_properties(name):
     ok4 = status4 == 1
     assert ok4.mean() > 0.75 and np.max(np.abs(T4[[3, 7, 11]][:, ok4] - target[[3, 7, 11]][:, ok4])) <= 1e-8
     del outside
+
+
+@pytest.mark.parametrize("name", ["c6", "c6_perturbed", "random_b", "random_d"])
+def test_oracle_ik_against_reference_loop(name):
+    """The restated loop against the REFERENCE's own computeLocalIk / computeWeigthedLocalIk (oracle/_ref: primitives_impl.h:1398-1468 and
+    frame_distance.h compiled where they lie; tick clock instead of the wall clock, stand-in box-QP for the un-vendored solve_quadprog)."""
+    oracle = _oracle()
+    if not oracle.build_ref():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    from oracle.oracle import OracleChain
+    d, oc, q_goal, target, q_seed = _ik_problem(name, 200, 21, 0.35)
+    rc = OracleChain(d, fast="ref")
+    qmin, qmax = np.full(d.n_inputs, -1.2), np.full(d.n_inputs, 1.2)   # some goals sit near / beyond the limits
+    # computeWeigthedLocalIk sizes its bound vector with m_joints_number instead of m_active_joints_number (PI.h:1453-1454): with a fixed
+    # joint in the chain the reference trips an Eigen size assertion, so the weighted loop is compared on chains without one
+    weights = (None, np.array([1.0, 1.0, 1.0, 0.5, 0.5, 0.5])) if d.n_joints == d.n_inputs else (None,)
+    for weight in weights:
+        sol, status, iters, err = oc.local_ik(target, q_seed, qmin, qmax, weight=weight, toll=1e-8, max_iter=25)
+        rsol, rstatus, riters, _ = rc.local_ik(target, q_seed, qmin, qmax, weight=weight, toll=1e-8, max_iter=25)
+        assert np.array_equal(status, rstatus)
+        ok = status == 1
+        assert ok.mean() > 0.5
+        assert np.array_equal(iters[ok], riters[ok])
+        assert np.max(np.abs(sol[:, ok] - rsol[:, ok])) <= 1e-9
 
 
 @pytest.mark.gpu
