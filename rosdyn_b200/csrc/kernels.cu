@@ -91,6 +91,21 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
     trig_all<NT>(qv, sv, cv);
   }
 
+  // regressor modes (HBM bound): the rates are all pulled into L2 up front (no register held), then loaded one link ahead of their use;
+  // measured slower for the FP64-bound torque walker (9.0 -> 8.5 G samples/s), which keeps the plain per-link loads
+  double dq_nx = 0.0, ddq_nx = 0.0;
+  if (NJ_T > 0 && kReg)
+  {
+#pragma unroll
+    for (int l = 1; l < NT; l++)
+    {
+      prefetch_in(in.dq, C.joint[l].in, in.ld, i);
+      prefetch_in(in.ddq, C.joint[l].in, in.ld, i);
+    }
+    dq_nx = ld_in(in.dq, C.joint[0].in, in.ld, i);
+    ddq_nx = ld_in(in.ddq, C.joint[0].in, in.ld, i);
+  }
+
 #pragma unroll
   for (int l = 0; l < (NJ_T > 0 ? NJ_T : nj); l++)
   {
@@ -116,8 +131,23 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
 
     if (kDyn)
     {
-      const double dql = ld_in(in.dq, J.in, in.ld, i);
-      const double ddql = ld_in(in.ddq, J.in, in.ld, i);
+      double dql, ddql;
+      if (NJ_T > 0 && kReg)  // requested one link earlier
+      {
+        dql = dq_nx;
+        ddql = ddq_nx;
+        if (l + 1 < NJ_T)
+        {
+          const int inn = C.joint[l + 1 < CAP ? l + 1 : 0].in;
+          dq_nx = ld_in(in.dq, inn, in.ld, i);
+          ddq_nx = ld_in(in.ddq, inn, in.ld, i);
+        }
+      }
+      else
+      {
+        dql = ld_in(in.dq, J.in, in.ld, i);
+        ddql = ld_in(in.ddq, J.in, in.ld, i);
+      }
       // getTwist (primitives_impl.h:1007-1008) and getDTwist (1116-1117) moved to the child frame
       v = rotT(R, cross_add(v, w, t));
       w = rotT(R, w);
@@ -445,6 +475,15 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
   double dq_nx = 0.0, ddq_nx = 0.0, dddq_nx = 0.0;  // rates of the next link (unrolled kernels)
   if (NJ_T > 0)
   {
+    // every rate the walk will need is pulled into L2 now (no register held), then loaded one link ahead of its use
+#pragma unroll
+    for (int l = 1; l < NT; l++)
+    {
+      const int inl = C.joint[l].in;
+      if (cVel) prefetch_in(in.dq, inl, in.ld, i);
+      if ((MASK & (K_DTWIST | K_DTWIST_LIN | K_TORQUE)) != 0 || cJer) prefetch_in(in.ddq, inl, in.ld, i);
+      if ((MASK & (K_DDTWIST | K_DDTWIST_LIN)) != 0) prefetch_in(in.dddq, inl, in.ld, i);
+    }
     const int in0 = C.joint[0].in;
     if (cVel) dq_nx = ld_in(in.dq, in0, in.ld, i);
     if ((MASK & (K_DTWIST | K_DTWIST_LIN | K_TORQUE)) != 0 || cJer) ddq_nx = ld_in(in.ddq, in0, in.ld, i);

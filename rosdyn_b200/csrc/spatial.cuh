@@ -139,6 +139,11 @@ __device__ __forceinline__ double ld_in(const double* p, int in, int64_t ld, int
 {
   return (p != nullptr && in >= 0) ? __ldcs(p + (int64_t)in * ld + i) : 0.0;
 }
+// L2 prefetch of an input that is needed later in the walk: the real load then finds the line on chip
+__device__ __forceinline__ void prefetch_in(const double* p, int in, int64_t ld, int64_t i)
+{
+  if (p != nullptr && in >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (int64_t)in * ld + i));
+}
 __device__ __forceinline__ void st_out(double* p, int64_t plane, int64_t ld, int64_t i, double v) { __stcs(p + plane * ld + i, v); }
 __device__ __forceinline__ void st3(double* p, int64_t plane, int64_t ld, int64_t i, V3 v)
 {
