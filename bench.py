@@ -374,7 +374,7 @@ def main():
             peak = max(peaks64["dmma_m8n8k4"], peaks64["dfma"])
         ach = S * flop / (ms * 1e-3 / args.steps) / 1e12
         tps = ncu_traffic_per_sample(f"gram_fused_kernel<{d.n_joints}>:{args.chain}")
-        # what the kernel actually executes: joints that never move (fixed / not an input) are folded out of the chain (gram_fused.cu:
+        # what the kernel actually executes: joints that never move (fixed / not an input) are folded out of the chain (fold.cpp:
         # fold_chain), and of the (P'+1)x(P'+1) augmented Gram matrix only the upper-triangular 8x8 tiles right of each row's first
         # non-zero column are multiplied (one DMMA m8n8k4 = 512 flop per tile per 4 samples)
         K = sum(1 for j in d.joints if j.input_index >= 0)

@@ -734,7 +734,7 @@ static cudaError_t launch_dyn_mode(const ChainHost& ch, const SamplesDev& in, do
   if (in.n <= 0) return cudaSuccess;
   const unsigned grid = grid_for(in.n);
   // torque and inertia do not depend on how the parameters are split between rigidly attached links: those modes walk the chain with the
-  // never-moving joints folded away and the parameters lumped (gram_fused.cu: fold_chain) -- C6 walks 6 links instead of 7
+  // never-moving joints folded away and the parameters lumped (fold.cpp: fold_chain) -- C6 walks 6 links instead of 7
   const bool folded = !(MODE & DYN_REGRESSOR) && ch.gram.fold_version == ch.model_version && ch.gram.fold.nj >= 1;
   const ChainDev<RDB_MAX_JOINTS>& H = folded ? ch.gram.fold : ch.host;
   bool rev = folded;  // all-revolute specialisation (torque / inertia on the folded chain only)

@@ -16,7 +16,7 @@ struct GramWorkspace
   int ctas = 0;
   double* fused_partials = nullptr;  // gram_fused.cu: per-CTA partial (P+1)x(P+1) upper-triangular tiles
   size_t fused_bytes = 0;
-  // gram_fused.cu: the chain with its never-moving joints folded away (fold_chain), rebuilt when the model changes
+  // fold.cpp: the chain with its never-moving joints folded away (fold_chain), rebuilt when the model changes
   ChainDev<RDB_MAX_JOINTS> fold;
   uint64_t fold_version = ~0ull;
   bool fold_identity = true;   // nothing was folded: no expansion step
@@ -91,7 +91,7 @@ cudaError_t launch_components_regressor(const ChainHost& ch, const SamplesDev& i
 cudaError_t launch_components_torque(const ChainHost& ch, const SamplesDev& in, const ComponentParams& prm, double* torque, int64_t ld_out,
                                      int accumulate, cudaStream_t st);
 cudaError_t fp64_peak(int kind, int reps, double* tflops);
-// gram_fused.cu: the chain with its never-moving joints folded away (ch.gram.fold); rebuilt by every model upload
+// fold.cpp: the chain with its never-moving joints folded away (ch.gram.fold); rebuilt by every model upload
 cudaError_t fold_chain(ChainHost& ch);
 // gram_fused.cu: cudaErrorNotSupported when the chain does not fit the fused kernel
 cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,

@@ -121,7 +121,7 @@ def test_gram_against_long_double_oracle(name, chains, torch):
 
 
 def _fold_case(case):
-    """Chains whose never-moving joints exercise every branch of the folded-chain Gram path (gram_fused.cu: fold_chain)."""
+    """Chains whose never-moving joints exercise every branch of the folded-chain Gram path (fold.cpp: fold_chain)."""
     from rosdyn_b200.descriptor import FIXED
     if case == "leading+double_interior":  # fixed joint at the base, two consecutive fixed joints inside, massive links everywhere
         d = fixtures.random_chain(909, 9, p_prismatic=0.3, p_fixed=0.0)
@@ -268,6 +268,33 @@ def test_large_batch_invariants(chains, torch):
     J = ch.getJacobian(q)
     v = ch.getTwist(q, dq)[-1]
     assert float((torch.einsum("rcs,cs->rs", J, dq) - v).abs().max()) <= RTOL * max(1.0, float(v.abs().max()))
+
+
+def test_gram_large_batch_invariants(chains, torch):
+    """Fused normal equations at BASELINE scale without a CPU oracle: G pi_nom == b (tau = Phi pi_nom), tau_sq == pi^T G pi, additivity over
+    shards (what the multi-GPU all-reduce relies on), and agreement with Phi^T Phi of the MATERIALISED regressor contracted by cuBLAS."""
+    for name in ("c6", "c7"):
+        d, ch, _ = chains(name)
+        n = 6_000_000
+        q, dq, ddq, _ = _inputs(torch, d.n_inputs, n, 0x5EED0002)
+        G, b, tt = ch.regressorGram(q, dq, ddq)
+        pi = torch.tensor(ch.getNominalParameters(), device="cuda")
+        assert float((G @ pi - b).abs().max()) <= 1e-10 * float(b.abs().max())
+        assert abs(float(pi @ G @ pi) - float(tt[0])) <= 1e-10 * float(tt[0])
+        assert bool((G == G.T).all())
+        h = 2_500_032
+        o = ch.regressorGram(q[:, :h].contiguous(), dq[:, :h].contiguous(), ddq[:, :h].contiguous())
+        o = ch.regressorGram(q[:, h:].contiguous(), dq[:, h:].contiguous(), ddq[:, h:].contiguous(), out=o)
+        scale = float(G.abs().max())
+        assert float((o[0] - G).abs().max()) <= 1e-11 * scale and float((o[1] - b).abs().max()) <= 1e-11 * float(b.abs().max())
+        m = 1_000_000
+        phi, tau = ch.getRegressor(q[:, :m].contiguous(), dq[:, :m].contiguous(), ddq[:, :m].contiguous(), with_torque=True)
+        F = phi.permute(2, 0, 1).reshape(m * d.n_inputs, -1)
+        Gm, bm, _ = ch.regressorGram(q[:, :m].contiguous(), dq[:, :m].contiguous(), ddq[:, :m].contiguous())
+        Fg = F.T @ F
+        assert float((Fg - Gm).abs().max()) <= 1e-10 * float(Fg.abs().max())
+        assert float((F.T @ tau.T.reshape(-1) - bm).abs().max()) <= 1e-10 * float(bm.abs().max())
+        del phi, F
 
 
 def test_chain_from_urdf(chains, torch):
