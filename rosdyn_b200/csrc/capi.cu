@@ -235,6 +235,7 @@ void rdb_chain_destroy(rdb_chain* chain)
   if (chain->gram.partials) cudaFree(chain->gram.partials);
   if (chain->gram.fused_partials) cudaFree(chain->gram.fused_partials);
   if (chain->gram.fold_dev) cudaFree(chain->gram.fold_dev);
+  if (chain->gram.ext_dev) cudaFree(chain->gram.ext_dev);
   GramHostPipe& hp = chain->gram_host;
   for (int k = 0; k < GramHostPipe::NSLOT; k++)
   {

@@ -176,9 +176,10 @@ cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_m
   {
     // fused warp-specialised kernel (gram_fused.cu) whenever the chain fits it; RDB_GRAM_IMPL=v0 forces the general pipeline
     static const bool force_v0 = [] { const char* e = getenv("RDB_GRAM_IMPL"); return e && e[0] == 'v'; }();
-    if (!force_v0 && P == Pr)
+    if (!force_v0)
     {
-      cudaError_t e = launch_gram_fused(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
+      cudaError_t e = (P == Pr) ? launch_gram_fused(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st)
+                                : launch_gram_fused_ext(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
       if (e != cudaErrorNotSupported) return e;
     }
   }

@@ -71,8 +71,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
       : "memory");
 }
 
-// geometry of the augmented Gram matrix and of a slot for a (folded) chain of NJ joints, all of them inputs
-template <int NJ>
+// geometry of the augmented Gram matrix and of a slot for a (folded) chain of NJ joints, all of them inputs.
+// X = 1 (cross mode, extended model [Phi | Phi_c]): every row carries GX_COLS component columns of its own joint after the tau column.
+constexpr int GX_COLS = 8;  // component columns per joint row (one 8-wide tile)
+template <int NJ, int X = 0>
 struct GramGeom
 {
   static constexpr int P = 10 * NJ;
@@ -85,7 +87,7 @@ struct GramGeom
   __host__ __device__ static constexpr int rowbase(int j)
   {
     int o = 0;
-    for (int i = 0; i < j; i++) o += (P + 1 - 10 * i) * 32;
+    for (int i = 0; i < j; i++) o += (P + 1 - 10 * i + (X ? GX_COLS : 0)) * 32;
     return o;
   }
   static constexpr int SLOT_DOUBLES = rowbase(NJ);
@@ -106,6 +108,58 @@ struct GramGeom
       if (owns(K, ts, par)) n += T - K;
     return n + (J - I);
   }
+  // cross mode: per joint row j the tiles (regular tile I, component tile of joint j), I = I0(j) .. T-1, then (component, component)
+  __host__ __device__ static constexpr int i0(int j) { return (10 * j) / 8; }
+  __host__ __device__ static constexpr int xtile(int j, int I)  // I == T: the (component, component) tile
+  {
+    int n = 0;
+    for (int k = 0; k < j; k++) n += T - i0(k) + 1;
+    return n + (I - i0(j));
+  }
+  __host__ __device__ static constexpr int nxt()
+  {
+    int n = 0;
+    for (int k = 0; k < NJ; k++) n += T - i0(k) + 1;
+    return n;
+  }
+  static constexpr int NXT = nxt();
+  __host__ __device__ static constexpr bool xowns(int j, int I, int ts, int par) { return ts == 1 || ((I == T ? j : I) & 1) == par; }
+  __host__ __device__ static constexpr int xlocal(int j, int I, int ts, int par)
+  {
+    int n = 0;
+    for (int k = 0; k <= j; k++)
+      for (int K = i0(k); K <= T; K++)
+      {
+        if (k == j && K == I) return n;
+        if (xowns(k, K, ts, par)) n++;
+      }
+    return n;
+  }
+  __host__ __device__ static constexpr int nxtiles(int ts, int par)
+  {
+    int n = 0;
+    for (int k = 0; k < NJ; k++)
+      for (int K = i0(k); K <= T; K++)
+        if (xowns(k, K, ts, par)) n++;
+    return n;
+  }
+};
+
+// components of the joints of the folded chain (cross mode): the columns they contribute to the row of their joint, one entry per column
+enum : int
+{
+  GXK_SAT = 1,    // FirstOrderPolynomialFriction column 0: clamp(omega / thr, -1, 1)           (friction_polynomial1.h:47-50)
+  GXK_OMEGA = 2,  // column 1 of both friction models: omega = clamp(Dq, -vmax, vmax)
+  GXK_SGN = 3,    // SecondOrderPolynomialFriction column 0: 0 / +-1 / omega / thr              (friction_polynomial2.h:44-53)
+  GXK_SQ = 4,     // SecondOrderPolynomialFriction column 2: omega^2 * (that sign)
+  GXK_Q = 5,      // IdealSpring column 0: q                                                    (ideal_spring.h:64-70)
+  GXK_ONE = 6     // IdealSpring column 1: 1
+};
+struct GramComps
+{
+  int32_t ncols[8];
+  int32_t kind[8][GX_COLS];
+  double thr[8][GX_COLS], vmax[8][GX_COLS];
 };
 
 // ---------------------------------------------------------------------------------------------- generator
@@ -130,12 +184,51 @@ __device__ __forceinline__ void gen_load(const ChainDev<NJ>& C, const SamplesDev
 // REV: every joint of the (folded) chain is revolute -- the usual arm.  The joint type is then a compile-time fact: no type selects, the
 // linear half of every joint screw is an exact zero that is never multiplied, and the projection of a link on its own joint (unit twist
 // [0; axis] at birth) loses its linear terms.
-template <int NJ, bool REV>
-__device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GenIn<NJ>& x, const SamplesDev& in, const double* __restrict__ tau_meas,
-                                              double* __restrict__ slot, int64_t i, int lane)
+// component columns of the joint with angle q and rate dq (element-wise), zero padded to one tile.  A rolled loop, kept OUT of the
+// walk so that the walk stays one basic block.
+__device__ __noinline__ void gram_component_columns(const int32_t* kind, const double* thr, const double* vmax, int nc, double q, double dq,
+                                                    double* __restrict__ o, int lane)
 {
-  using G = GramGeom<NJ>;
+#pragma unroll 1
+  for (int c = 0; c < GX_COLS; c++)
+  {
+    double val = 0.0;
+    if (c < nc)
+    {
+      const int kd = kind[c];
+      const double th = thr[c], vm = vmax[c];
+      const double omega = fmin(fmax(dq, -vm), vm);
+      if (kd == GXK_OMEGA) val = omega;
+      else if (kd == GXK_Q) val = q;
+      else if (kd == GXK_ONE) val = 1.0;
+      else
+      {
+        const double r = omega / th;
+        if (kd == GXK_SAT) val = fmin(fmax(r, -1.0), 1.0);
+        else
+        {
+          const double sg = omega == 0.0 ? 0.0 : (omega > th ? 1.0 : (omega < -th ? -1.0 : r));
+          val = kd == GXK_SGN ? sg : omega * omega * sg;
+        }
+      }
+    }
+    o[c * 32 + (lane ^ (4 * (c & 3)))] = val;
+  }
+}
+
+template <int NJ, bool REV, int X>
+__device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramComps& comps, const GenIn<NJ>& x, const SamplesDev& in,
+                                              const double* __restrict__ tau_meas, double* __restrict__ slot, int64_t i, int lane)
+{
+  using G = GramGeom<NJ, X>;
   constexpr int P = G::P;
+  if (X)
+  {
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+      gram_component_columns(comps.kind[j], comps.thr[j], comps.vmax[j], comps.ncols[j], x.q[j], x.dq[j],
+                             slot + G::rowbase(j) + (P + 1 - 10 * j) * 32, lane);
+  }
   V3 U[NJ], S[NJ];
   double tau[NJ];
   V3 v = v3(0, 0, 0), w = v3(0, 0, 0), a = v3(0, 0, 0), al = v3(0, 0, 0);
@@ -233,20 +326,24 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GenIn
 }
 
 // lanes past the end of the batch (last group only): their rows become exact zeros
-template <int NJ>
+template <int NJ, int X>
 __device__ __noinline__ void gram_zero_lane(double* __restrict__ slot, int lane)
 {
-  using G = GramGeom<NJ>;
+  using G = GramGeom<NJ, X>;
   for (int j = 0; j < NJ; j++)
+  {
     for (int c = 10 * j; c <= G::P; c++) slot[G::rowbase(j) + (c - 10 * j) * 32 + (lane ^ (4 * (c & 3)))] = 0.0;
+    if (X)
+      for (int c = 0; c < GX_COLS; c++) slot[G::rowbase(j) + (G::P + 1 - 10 * j + c) * 32 + (lane ^ (4 * (c & 3)))] = 0.0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- MMA side
 // B fragments of one k-step (4 samples of joint row J, k-step kk of the slot): lane (g, t) holds column 8 I + g of sample 4 kk + t
-template <int NJ, int J>
+template <int NJ, int J, int X = 0>
 __device__ __forceinline__ void gram_load_frags(const double* __restrict__ slot, int kk, int lane, double (&b)[GramGeom<NJ>::T])
 {
-  using G = GramGeom<NJ>;
+  using G = GramGeom<NJ, X>;
   constexpr int P = G::P, T = G::T, c0 = 10 * J, I0 = c0 / 8;
   const int g = lane >> 2, t = lane & 3;
   const double* rowp = slot + G::rowbase(J) + ((4 * kk + t) ^ (4 * (g & 3)));
@@ -362,11 +459,118 @@ __device__ __forceinline__ void gram_mma_role(const SamplesDev& in, double* smem
   }
 }
 
-template <int NJ, int SLOTS, bool REV>
-__device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const SamplesDev& in, const double* __restrict__ tau_meas, double* smem,
-                                              GramBars* bars, int s, int lane, int dbg)
+// ---------------------------------------------------------------------------------------------- MMA side, cross mode
+// Extended model [Phi | Phi_c]: the component columns of joint j are non-zero in the row of joint j only, so
+//   Phi^T Phi_c [:, comps of j] = sum_s Phi_row_j(s)^T phi_c,j(s)      (one extra 8-wide tile per joint row),
+// Phi_c^T Phi_c is block diagonal per joint and Phi_c^T tau rides in the tau column of the last regular tile.  The rigid-body block comes
+// from the X = 0 kernel; this mode accumulates only the cross tiles (NXT of them) with the same slots, k-split and software pipelining.
+template <int NJ, int J>
+__device__ __forceinline__ double gram_load_xfrag(const double* __restrict__ slot, int kk, int lane)
 {
-  using G = GramGeom<NJ>;
+  using G = GramGeom<NJ, 1>;
+  const int g = lane >> 2, t = lane & 3;
+  return slot[G::rowbase(J) + (G::P + 1 - 10 * J + g) * 32 + ((4 * kk + t) ^ (4 * (g & 3)))];
+}
+template <int NJ, int PAR, int J>
+__device__ __forceinline__ void gram_cross_step(const double (&b)[GramGeom<NJ>::T], double bx, double (&acc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2])
+{
+  using G = GramGeom<NJ, 1>;
+#pragma unroll
+  for (int I = 0; I < G::T; I++)
+  {
+    if (I < G::i0(J) || !G::xowns(J, I, GF_TS, PAR)) continue;
+    dmma884f(acc[G::xlocal(J, I, GF_TS, PAR)][0], acc[G::xlocal(J, I, GF_TS, PAR)][1], b[I], bx);
+  }
+  if (G::xowns(J, G::T, GF_TS, PAR)) dmma884f(acc[G::xlocal(J, G::T, GF_TS, PAR)][0], acc[G::xlocal(J, G::T, GF_TS, PAR)][1], bx, bx);
+}
+template <int NJ, int PAR, int STEP>
+__device__ __forceinline__ void gram_cross_steps(const double* __restrict__ slot, int ks, int lane, const double (&bcur)[GramGeom<NJ>::T], double bxcur,
+                                                 double (&acc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2])
+{
+  using G = GramGeom<NJ, 1>;
+  constexpr int J = STEP / G::KPW;
+  if constexpr (STEP + 1 < G::NSTEPS)
+  {
+    double bnext[G::T];
+    constexpr int JN = (STEP + 1) / G::KPW;
+    const int kn = ks * G::KPW + (STEP + 1) % G::KPW;
+    gram_load_frags<NJ, JN, 1>(slot, kn, lane, bnext);
+    const double bxn = gram_load_xfrag<NJ, JN>(slot, kn, lane);
+    gram_cross_step<NJ, PAR, J>(bcur, bxcur, acc);
+    gram_cross_steps<NJ, PAR, STEP + 1>(slot, ks, lane, bnext, bxn, acc);
+  }
+  else
+    gram_cross_step<NJ, PAR, J>(bcur, bxcur, acc);
+}
+
+template <int NJ, int SLOTS, int PAR>
+__device__ __forceinline__ void gram_cross_role(const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane, int dbg)
+{
+  using G = GramGeom<NJ, 1>;
+  constexpr int NXP = G::nxtiles(GF_TS, PAR);
+  double acc[NXP][2];
+#pragma unroll
+  for (int k = 0; k < NXP; k++) acc[k][0] = acc[k][1] = 0.0;
+  const int64_t ngroups = (in.n + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * SLOTS;
+  uint32_t parity = 0;
+  for (int64_t base = (int64_t)blockIdx.x * SLOTS; base < ngroups; base += stride, parity ^= 1)
+  {
+#pragma unroll 1
+    for (int s = 0; s < SLOTS; s++)
+    {
+      if (base + s >= ngroups) break;
+      const double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
+      mbar_wait(&bars->full[s], parity);
+      if (!(dbg & 2))
+      {
+        double b0[G::T];
+        gram_load_frags<NJ, 0, 1>(slot, ks * G::KPW, lane, b0);
+        const double bx0 = gram_load_xfrag<NJ, 0>(slot, ks * G::KPW, lane);
+        gram_cross_steps<NJ, PAR, 0>(slot, ks, lane, b0, bx0, acc);
+      }
+      if (base + s + stride < ngroups)
+      {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->empty[s]);
+      }
+    }
+  }
+  bar_sync(GF_BAR_REDUCE, 32 * GF_MMA_WARPS);
+  const int g = lane >> 2, t = lane & 3;
+  for (int w = 0; w < GF_KSPLIT; w++)
+  {
+    if (ks == w)
+    {
+#pragma unroll
+      for (int j = 0; j < NJ; j++)
+#pragma unroll
+        for (int I = 0; I <= G::T; I++)
+        {
+          if (I < G::i0(j) || !G::xowns(j, I, GF_TS, PAR)) continue;
+          double* o = smem + G::xtile(j, I) * 64 + g * 8 + 2 * t;
+          const int k = G::xlocal(j, I, GF_TS, PAR);
+          if (w == 0)
+          {
+            o[0] = acc[k][0];
+            o[1] = acc[k][1];
+          }
+          else
+          {
+            o[0] += acc[k][0];
+            o[1] += acc[k][1];
+          }
+        }
+    }
+    bar_sync(GF_BAR_REDUCE, 32 * GF_MMA_WARPS);
+  }
+}
+
+template <int NJ, int SLOTS, bool REV, int X>
+__device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const GramComps& comps, const SamplesDev& in,
+                                              const double* __restrict__ tau_meas, double* smem, GramBars* bars, int s, int lane, int dbg)
+{
+  using G = GramGeom<NJ, X>;
   double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
   const int64_t ngroups = (in.n + 31) / 32;
   const int64_t stride = (int64_t)gridDim.x * SLOTS;
@@ -381,20 +585,20 @@ __device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const Sampl
     mbar_wait(&bars->empty[s], parity);  // consumers released the slot
     if (!(dbg & 1))
     {
-      gram_generate<NJ, REV>(C, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
-      if (i >= in.n) gram_zero_lane<NJ>(slot, lane);
+      gram_generate<NJ, REV, X>(C, comps, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
+      if (i >= in.n) gram_zero_lane<NJ, X>(slot, lane);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars->full[s]);
   }
 }
 
-template <int NJ, int SLOTS, bool REV>
+template <int NJ, int SLOTS, bool REV, int X>
 __global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
-    gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const double* __restrict__ tau_meas, double* __restrict__ partial,
-                      const int dbg)
+    gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const __grid_constant__ GramComps comps, const SamplesDev in,
+                      const double* __restrict__ tau_meas, double* __restrict__ partial, const int dbg)
 {
-  using G = GramGeom<NJ>;
+  using G = GramGeom<NJ, X>;
   extern __shared__ __align__(16) double smem[];
   __shared__ GramBars bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -411,16 +615,25 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
   // group of (iteration it, CTA, slot s): (it*gridDim.x + blockIdx.x)*SLOTS + s ; generator warp s fills slot s
   if (warp >= GF_MMA_WARPS)
   {
-    gram_gen_role<NJ, SLOTS, REV>(C, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
+    gram_gen_role<NJ, SLOTS, REV, X>(C, comps, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
     return;
   }
   // ------------------------------------------------ MMA warps: k-split index = warp % 4 (its SM sub-partition), tile-row parity = warp / 4
   const int mma_id = warp;
   const int ks = mma_id % GF_KSPLIT;
-  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, SLOTS, 0>(in, smem, &bars, ks, lane, dbg);
-  else gram_mma_role<NJ, SLOTS, 1>(in, smem, &bars, ks, lane, dbg);
-  double* out = partial + (size_t)blockIdx.x * G::NT * 64;
-  for (int k = mma_id * 32 + lane; k < G::NT * 64; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
+  constexpr int NOUT = (X ? G::NXT : G::NT) * 64;
+  if (X)
+  {
+    if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_cross_role<NJ, SLOTS, 0>(in, smem, &bars, ks, lane, dbg);
+    else gram_cross_role<NJ, SLOTS, 1>(in, smem, &bars, ks, lane, dbg);
+  }
+  else
+  {
+    if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, SLOTS, 0>(in, smem, &bars, ks, lane, dbg);
+    else gram_mma_role<NJ, SLOTS, 1>(in, smem, &bars, ks, lane, dbg);
+  }
+  double* out = partial + (size_t)blockIdx.x * NOUT;
+  for (int k = mma_id * 32 + lane; k < NOUT; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
 }
 
 // fixed-order sum of the per-CTA partials -> gram (full symmetric, column-major), rhs, tau_sq
@@ -502,6 +715,17 @@ static ChainDev<NJ> narrow_g(const ChainDev<RDB_MAX_JOINTS>& h)
   return c;
 }
 
+static cudaError_t grow(double*& p, size_t& have, size_t need)
+{
+  if (have >= need) return cudaSuccess;
+  if (p) cudaFree(p);
+  p = nullptr;
+  have = 0;
+  cudaError_t e = cudaMalloc(&p, need);
+  if (e == cudaSuccess) have = need;
+  return e;
+}
+
 template <int NJ, int SLOTS, bool REV>
 static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
                                    int accumulate, cudaStream_t st)
@@ -509,23 +733,18 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const do
   using G = GramGeom<NJ>;
   const size_t smem = sizeof(double) * (size_t)std::max(G::SLOT_DOUBLES * SLOTS, G::NT * 64);
   {
-    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS, REV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   static const int dbg = [] { const char* e = getenv("RDB_GRAM_DEBUG"); return e ? atoi(e) : 0; }();  // 1: skip generation, 2: skip MMA (timing experiments only)
   const int64_t ngroups = (in.n + 31) / 32;
   const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + SLOTS - 1) / SLOTS);
-  const size_t need = sizeof(double) * (size_t)ch.sm_count * G::NT * 64;
-  if (ch.gram.fused_bytes < need)
   {
-    if (ch.gram.fused_partials) cudaFree(ch.gram.fused_partials);
-    ch.gram.fused_partials = nullptr;
-    ch.gram.fused_bytes = 0;
-    cudaError_t e = cudaMalloc(&ch.gram.fused_partials, need);
+    cudaError_t e = grow(ch.gram.fused_partials, ch.gram.fused_bytes, sizeof(double) * (size_t)ch.sm_count * G::NT * 64);
     if (e != cudaSuccess) return e;
-    ch.gram.fused_bytes = need;
   }
-  gram_fused_kernel<NJ, SLOTS, REV><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), in, tau_meas, ch.gram.fused_partials, dbg);
+  gram_fused_kernel<NJ, SLOTS, REV, 0><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), GramComps{}, in, tau_meas,
+                                                                              ch.gram.fused_partials, dbg);
   count_launch();
   if (ch.gram.fold_identity)
   {
@@ -549,10 +768,10 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const do
 }
 
 // slots that fit the shared memory of an SM (227 KB minus 1 KB of barriers / static data)
-template <int NJ>
+template <int NJ, int X = 0>
 constexpr int gf_slots()
 {
-  return std::min<int>(GF_MAX_SLOTS, (int)((227 * 1024 - 1024) / (sizeof(double) * GramGeom<NJ>::SLOT_DOUBLES)));
+  return std::min<int>(GF_MAX_SLOTS, (int)((227 * 1024 - 1024) / (sizeof(double) * GramGeom<NJ, X>::SLOT_DOUBLES)));
 }
 
 // returns cudaErrorNotSupported when the chain does not fit the fused kernel (caller falls back to the general pipeline)
@@ -572,6 +791,175 @@ cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double*
 #undef X
   }
   return cudaErrorNotSupported;
+}
+
+// ---------------------------------------------------------------------------------------------- extended model [Phi | Phi_c]
+// sum of the per-CTA cross partials in a fixed order
+__global__ void gram_cross_reduce_kernel(const double* __restrict__ partial, int nparts, int n, double* __restrict__ sum)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; p++) s += partial[(size_t)p * n + e];
+  sum[e] = s;
+}
+
+// the rigid-body block (P x P, rhs, tau_sq) into the extended normal equations (Pt x Pt)
+__global__ void gram_ext_scatter_kernel(const double* __restrict__ G, const double* __restrict__ b, const double* __restrict__ ts, int P, int Pt,
+                                        double* __restrict__ gram, double* __restrict__ rhs, double* __restrict__ tau_sq, int accumulate)
+{
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P * (P + 1)) return;
+  const int a = e / (P + 1), c = e % (P + 1);
+  if (e == P && tau_sq) *tau_sq = accumulate ? *tau_sq + *ts : *ts;
+  if (c == P)
+  {
+    rhs[a] = accumulate ? rhs[a] + b[a] : b[a];
+    return;
+  }
+  const double v = G[(size_t)c * P + a];
+  gram[(size_t)c * Pt + a] = accumulate ? gram[(size_t)c * Pt + a] + v : v;
+}
+
+// cross blocks of the extended normal equations from the reduced cross tiles:
+//   gram[a][P + cc] (and its mirror) = sum_c T[la][c][pa] X(10 ka + c ; joint, slot of cc)     a < P   (fold expansion of the rigid column)
+//   rhs[P + cc] = X(P' ; joint, slot)                                                          (tau column of the last regular tile)
+//   gram[P + c2][P + cc] = XX(joint)[slot2][slot] when both components act on the same joint, else 0
+// xj / xs: reduced joint and slot of every component column.  One thread per (a in 0 .. P + Pc, cc).
+__global__ void gram_cross_finish_kernel(const double* __restrict__ X, const double* __restrict__ Tm, const int32_t* __restrict__ kof,
+                                         const int32_t* __restrict__ xj, const int32_t* __restrict__ xs, int nj, int njr, int Pc,
+                                         double* __restrict__ gram, double* __restrict__ rhs, int accumulate)
+{
+  const int P = 10 * nj, Pr = 10 * njr, Pt = P + Pc, T = (Pr + 1 + 7) / 8;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (P + 1 + Pc) * Pc) return;
+  const int a = e / Pc, cc = e % Pc;
+  const int j = xj[cc], g = xs[cc];
+  int tb = 0;  // first cross tile of joint j
+  for (int k = 0; k < j; k++) tb += T - (10 * k) / 8 + 1;
+  const int i0 = (10 * j) / 8;
+  auto xval = [&](int col) -> double {  // reduced regular column `col` (<= Pr) against (j, g)
+    const int I = col >> 3;
+    return I < i0 ? 0.0 : X[(size_t)(tb + I - i0) * 64 + (col & 7) * 8 + g];
+  };
+  if (a < P)
+  {
+    double s = 0.0;
+    if (kof)
+    {
+      const int la = a / 10, pa = a % 10, ka = kof[la];
+      if (ka >= 0)
+        for (int c = 0; c < 10; c++) s = fma(Tm[(size_t)la * 100 + c * 10 + pa], xval(10 * ka + c), s);
+    }
+    else
+      s = xval(a);
+    double* o = gram + (size_t)(P + cc) * Pt + a;
+    const double v = accumulate ? *o + s : s;
+    *o = v;
+    gram[(size_t)a * Pt + P + cc] = v;
+  }
+  else if (a == P)
+  {
+    const double s = xval(Pr);
+    rhs[P + cc] = accumulate ? rhs[P + cc] + s : s;
+  }
+  else
+  {
+    const int c2 = a - P - 1;
+    const double s = (xj[c2] == j) ? X[(size_t)(tb + T - i0) * 64 + xs[c2] * 8 + g] : 0.0;
+    double* o = gram + (size_t)(P + cc) * Pt + P + c2;
+    *o = accumulate ? *o + s : s;
+  }
+}
+
+template <int NJ, int SLOTS, bool REV>
+static cudaError_t launch_cross_nj(ChainHost& ch, const GramComps& gc, const SamplesDev& in, const double* tau_meas, double* xpartial, double* xsum,
+                                   cudaStream_t st)
+{
+  using G = GramGeom<NJ, 1>;
+  const size_t smem = sizeof(double) * (size_t)std::max(G::SLOT_DOUBLES * SLOTS, G::NXT * 64);
+  cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS, REV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t ngroups = (in.n + 31) / 32;
+  const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + SLOTS - 1) / SLOTS);
+  gram_fused_kernel<NJ, SLOTS, REV, 1><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), gc, in, tau_meas, xpartial, 0);
+  count_launch();
+  gram_cross_reduce_kernel<<<(G::NXT * 64 + 255) / 256, 256, 0, st>>>(xpartial, grid, G::NXT * 64, xsum);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// Normal equations of the extended model: the rigid-body block from the X = 0 kernel, the component blocks from the cross mode.
+// cudaErrorNotSupported: more than 7 moving joints, a component on an input no chain joint feeds, or more than GX_COLS component columns
+// on one joint (caller falls back to the general pipeline).
+cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
+                                  int accumulate, cudaStream_t st)
+{
+  if (in.n <= 0 || ch.gram.fold_version != ch.model_version) return cudaErrorNotSupported;
+  const ChainDev<RDB_MAX_JOINTS>& F = ch.gram.fold;
+  const int K = F.nj, nj = ch.host.nj, P = 10 * nj, Pc = ch.comps.cols, Pt = P + Pc;
+  if (K < 1 || K > 7 || Pc <= 0) return cudaErrorNotSupported;
+  GramComps gc{};
+  std::vector<int32_t> xmap(2 * (size_t)Pc, 0);
+  for (int k = 0; k < ch.comps.n; k++)
+  {
+    const ComponentDev& c = ch.comps.c[k];
+    int j = -1;
+    for (int r = 0; r < K; r++)
+      if (F.joint[r].in == c.in) j = r;
+    if (j < 0 || gc.ncols[j] + c.ncols > GX_COLS) return cudaErrorNotSupported;
+    const int kinds[3][3] = {{GXK_SAT, GXK_OMEGA, 0}, {GXK_SGN, GXK_OMEGA, GXK_SQ}, {GXK_Q, GXK_ONE, 0}};
+    const int row = c.type == RDB_COMPONENT_FRICTION_POLY1 ? 0 : (c.type == RDB_COMPONENT_FRICTION_POLY2 ? 1 : 2);
+    for (int p = 0; p < c.ncols; p++)
+    {
+      const int g = gc.ncols[j]++;
+      gc.kind[j][g] = kinds[row][p];
+      gc.thr[j][g] = c.thr;
+      gc.vmax[j][g] = c.vmax;
+      xmap[c.col + p] = j;
+      xmap[Pc + c.col + p] = g;
+    }
+  }
+  bool rev = true;
+  for (int j = 0; j < K; j++) rev = rev && F.joint[j].type == RDB_JOINT_REVOLUTE;
+  const int T = (10 * K + 1 + 7) / 8;
+  int nxt = 0;
+  for (int j = 0; j < K; j++) nxt += T - (10 * j) / 8 + 1;
+  // workspace: rigid block (P*P + P + 1) | cross sums (nxt*64) | cross partials (sm_count*nxt*64) | component map (2 Pc ints)
+  const size_t n_rigid = (size_t)P * P + P + 1, n_sum = (size_t)nxt * 64, n_part = (size_t)ch.sm_count * nxt * 64;
+  cudaError_t e = grow(ch.gram.ext_dev, ch.gram.ext_bytes, sizeof(double) * (n_rigid + n_sum + n_part) + sizeof(int32_t) * 2 * (size_t)Pc);
+  if (e != cudaSuccess) return e;
+  double* Gt = ch.gram.ext_dev;
+  double* bt = Gt + (size_t)P * P;
+  double* tst = bt + P;
+  double* xsum = tst + 1;
+  double* xpart = xsum + n_sum;
+  int32_t* dmap = reinterpret_cast<int32_t*>(xpart + n_part);
+  e = cudaMemcpyAsync(dmap, xmap.data(), sizeof(int32_t) * xmap.size(), cudaMemcpyHostToDevice, st);  // pageable source: staged before return
+  if (e != cudaSuccess) return e;
+  // rigid-body block
+  e = launch_gram_fused(ch, in, tau_meas, Gt, bt, tst, 0, st);
+  if (e != cudaSuccess) return e;
+  gram_ext_scatter_kernel<<<(P * (P + 1) + 255) / 256, 256, 0, st>>>(Gt, bt, tst, P, Pt, gram, rhs, tau_sq, accumulate);
+  count_launch();
+  // component blocks
+  switch (K)
+  {
+#define X(N)                                                                                     \
+  case N:                                                                                        \
+    e = rev ? launch_cross_nj<N, gf_slots<N, 1>(), true>(ch, gc, in, tau_meas, xpart, xsum, st) \
+            : launch_cross_nj<N, gf_slots<N, 1>(), false>(ch, gc, in, tau_meas, xpart, xsum, st); \
+    break;
+    X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+#undef X
+  }
+  if (e != cudaSuccess) return e;
+  const double* Tm = ch.gram.fold_identity ? nullptr : ch.gram.fold_dev;
+  const int32_t* kof = ch.gram.fold_identity ? nullptr
+                                             : reinterpret_cast<const int32_t*>(ch.gram.fold_dev + (size_t)nj * 100 + (size_t)(10 * K + 1) * (10 * K + 1));
+  gram_cross_finish_kernel<<<((P + 1 + Pc) * Pc + 127) / 128, 128, 0, st>>>(xsum, Tm, kof, dmap, dmap + Pc, nj, K, Pc, gram, rhs, accumulate);
+  count_launch();
+  return cudaGetLastError();
 }
 
 }  // namespace rdb

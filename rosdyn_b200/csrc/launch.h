@@ -22,6 +22,8 @@ struct GramWorkspace
   bool fold_identity = true;   // nothing was folded: no expansion step
   double* fold_dev = nullptr;  // parameter maps T | reduced normal equations | link -> reduced link
   size_t fold_bytes = 0;
+  double* ext_dev = nullptr;   // extended model: rigid-body block | cross-tile sums | cross partials | component map
+  size_t ext_bytes = 0;
 };
 
 // persistent pipeline of rdb_regressor_gram_batch_host (capi.cu)
@@ -96,6 +98,9 @@ cudaError_t fold_chain(ChainHost& ch);
 // gram_fused.cu: cudaErrorNotSupported when the chain does not fit the fused kernel
 cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
                               int accumulate, cudaStream_t st);
+// same for the extended model [Phi | Phi_c] (gram is Pt x Pt, Pt = 10 nJ + component columns)
+cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
+                                  int accumulate, cudaStream_t st);
 
 enum : int
 {
