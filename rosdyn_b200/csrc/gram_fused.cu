@@ -184,8 +184,8 @@ __device__ __forceinline__ void gen_load(const ChainDev<NJ>& C, const SamplesDev
 // REV: every joint of the (folded) chain is revolute -- the usual arm.  The joint type is then a compile-time fact: no type selects, the
 // linear half of every joint screw is an exact zero that is never multiplied, and the projection of a link on its own joint (unit twist
 // [0; axis] at birth) loses its linear terms.
-// component columns of the joint with angle q and rate dq (element-wise), zero padded to one tile.  A rolled loop, kept OUT of the
-// walk so that the walk stays one basic block.
+// component columns of the joint with angle q and rate dq (element-wise), zero padded to one tile.  A rolled loop in a real function,
+// called after the walk: the walk stays one basic block and no walker state has to survive the calls.
 __device__ __noinline__ void gram_component_columns(const int32_t* kind, const double* thr, const double* vmax, int nc, double q, double dq,
                                                     double* __restrict__ o, int lane)
 {
@@ -222,13 +222,7 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramC
 {
   using G = GramGeom<NJ, X>;
   constexpr int P = G::P;
-  if (X)
-  {
-#pragma unroll
-    for (int j = 0; j < NJ; j++)
-      gram_component_columns(comps.kind[j], comps.thr[j], comps.vmax[j], comps.ncols[j], x.q[j], x.dq[j],
-                             slot + G::rowbase(j) + (P + 1 - 10 * j) * 32, lane);
-  }
+
   V3 U[NJ], S[NJ];
   double tau[NJ];
   V3 v = v3(0, 0, 0), w = v3(0, 0, 0), a = v3(0, 0, 0), al = v3(0, 0, 0);
@@ -322,6 +316,14 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramC
   {
     const double tv = tau_meas ? __ldcs(tau_meas + (int64_t)C.joint[j].in * in.ld + i) : tau[j];
     slot[G::rowbase(j) + (P - 10 * j) * 32 + (lane ^ (4 * (P & 3)))] = tv;
+  }
+  if (X)
+  {
+    // after the walk, when almost nothing is live across the calls; q_j / Dq_j are read again (L2 hits)
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+      gram_component_columns(comps.kind[j], comps.thr[j], comps.vmax[j], comps.ncols[j], ld_in(in.q, C.joint[j].in, in.ld, i),
+                             ld_in(in.dq, C.joint[j].in, in.ld, i), slot + G::rowbase(j) + (P + 1 - 10 * j) * 32, lane);
   }
 }
 
