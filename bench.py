@@ -256,10 +256,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     old_affinity = bind_to_gpu_numa_node(local) if world > 1 else None
+    # rank 0 prints ONE JSON line on stdout: everything else that lands on file descriptor 1 from here on (NCCL prints its version banner
+    # there) is sent to stderr, and the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO writes it to stdout) out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and "NCCL_DEBUG_FILE" not in os.environ:
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
 
     d = fixtures.by_name(args.chain)
@@ -415,7 +417,8 @@ def main():
                        "parallelism": f"{world} x independent sample shards" + (" + NCCL all-reduce of the partials" if gram and world > 1 else "")},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
