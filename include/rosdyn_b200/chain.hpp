@@ -206,6 +206,19 @@ public:
   {
     check(rdb_local_ik_batch(m_h, n, ld, target, seed, q_min, q_max, weight, toll, max_iter, sol, status, iterations, error_norm, stream));
   }
+  // Chain::getMultiplicity (primitives_impl.h:1470-1517): multi-turn images of q inside [q_min, q_max]; joint_type_of_input[i] = RDB_JOINT_*
+  static std::vector<std::vector<double>> getMultiplicity(const std::vector<int32_t>& joint_type_of_input, const std::vector<double>& q,
+                                                          const std::vector<double>& q_min, const std::vector<double>& q_max)
+  {
+    const int32_t n = (int32_t)q.size();
+    int64_t count = 0;
+    rdb_multiplicity(n, joint_type_of_input.data(), q.data(), q_min.data(), q_max.data(), nullptr, 0, &count);
+    std::vector<double> flat((size_t)count * n);
+    check(rdb_multiplicity(n, joint_type_of_input.data(), q.data(), q_min.data(), q_max.data(), flat.data(), count, &count));
+    std::vector<std::vector<double>> out((size_t)count);
+    for (int64_t k = 0; k < count; k++) out[k].assign(flat.begin() + k * n, flat.begin() + (k + 1) * n);
+    return out;
+  }
   // additive joint components (friction_polynomial1.h, friction_polynomial2.h, ideal_spring.h) as extra regressor columns
   unsigned int setComponents(const std::vector<rdb_component_desc>& components)
   {

@@ -401,6 +401,27 @@ void oracle_local_ik_batch(void* cv, int64_t n, int64_t ld, const double* target
   }
 }
 
+// Chain::getMultiplicity of the reference (primitives_impl.h:1470-1517); limits through the urdf model as for the IK
+int64_t oracle_multiplicity(void* cv, const double* q, const double* q_min, const double* q_max, double* out, int64_t capacity)
+{
+  RefChain* rc = static_cast<RefChain*>(cv);
+  for (size_t j = 0; j < rc->ujoints.size(); j++)
+  {
+    const int r = rc->input_of_joint[j];
+    if (r < 0 || r >= rc->n_in) continue;
+    rc->ujoints[j]->limits->lower = q_min[r];
+    rc->ujoints[j]->limits->upper = q_max[r];
+  }
+  rosdyn::ChainPtr ch = rosdyn::createChain(*rc->model, rc->base_name, rc->tool_name, rc->gravity);
+  ch->setInputJointsName(rc->input_names);
+  Eigen::VectorXd v(rc->n_in);
+  for (int r = 0; r < rc->n_in; r++) v(r) = q[r];
+  const std::vector<Eigen::VectorXd> all = ch->getMultiplicity(v);
+  for (size_t k = 0; k < all.size() && (int64_t)k < capacity; k++)
+    for (int r = 0; r < rc->n_in; r++) out[k * rc->n_in + r] = all[k](r);
+  return (int64_t)all.size();
+}
+
 void oracle_regressor_gram(const void* cv, int64_t n, int64_t ld, const double* q, const double* dq, const double* ddq, const double* tau_meas,
                            double* gram, double* rhs, double* tau_sq)
 {

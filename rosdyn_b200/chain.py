@@ -325,6 +325,18 @@ class Chain:
 
     computeWeigthedLocalIk = computeLocalIk  # the reference's spelling (PI.h:1435); pass weight=
 
+    def getMultiplicity(self, q, q_min, q_max):
+        """Chain::getMultiplicity (PI.h:1470-1517): the multi-turn images q + 2 pi k of a joint vector inside the limits (revolute input joints
+        only), in the reference's order; host arrays.  Returns an array [count][n_act]."""
+        return multiplicity(self._input_joint_types(), q, q_min, q_max)
+
+    def _input_joint_types(self):
+        t = [0] * self.n_in
+        for j in self.desc.joints:
+            if 0 <= j.input_index < self.n_in:
+                t[j.input_index] = int(j.type)
+        return t
+
     def getTransformationLink(self, q, link_name):
         """Chain::getTransformationLink (PI.h:912-925)."""
         names = self.getLinksName()
@@ -569,3 +581,20 @@ def createChain(model, base_frame: Optional[str] = None, tool_frame: Optional[st
         if e.status == _lib.RDB_ERR_INVALID_ARG:
             return None
         raise
+
+
+def multiplicity(joint_type_of_input, q, q_min, q_max):
+    """rdb_multiplicity (host only, no device needed): see Chain.getMultiplicity."""
+    from ._lib import load
+    lib = load()
+    n = len(joint_type_of_input)
+    ty = (ctypes.c_int32 * max(n, 1))(*[int(v) for v in joint_type_of_input])
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (q, q_min, q_max)]
+    if any(a.shape != (n,) for a in arrs):
+        raise ValueError("Input data dimensions mismatch")
+    dp = ctypes.POINTER(ctypes.c_double)
+    cnt = ctypes.c_int64(0)
+    lib.rdb_multiplicity(n, ty, *[a.ctypes.data_as(dp) for a in arrs], None, 0, ctypes.byref(cnt))  # first call: how many
+    out = np.zeros((cnt.value, n))
+    check(lib.rdb_multiplicity(n, ty, *[a.ctypes.data_as(dp) for a in arrs], out.ctypes.data_as(dp), cnt.value, ctypes.byref(cnt)))
+    return out

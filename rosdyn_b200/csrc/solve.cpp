@@ -105,3 +105,37 @@ extern "C" rdb_status rdb_normal_equations_solve(int32_t P, const double* gram, 
   }
   return RDB_OK;
 }
+
+// Chain::getMultiplicity (primitives_impl.h:1470-1517): the multi-turn images of q inside the joint limits
+extern "C" rdb_status rdb_multiplicity(int32_t n, const int32_t* joint_type_of_input, const double* q, const double* q_min, const double* q_max,
+                                       double* out, int64_t capacity, int64_t* count)
+{
+  if (n < 0 || !count || (n > 0 && (!joint_type_of_input || !q || !q_min || !q_max))) return RDB_ERR_INVALID_ARG;
+  const double two_pi = 2.0 * 3.14159265358979323846;  // 2*M_PI
+  std::vector<std::vector<double>> ax((size_t)n);
+  for (int i = 0; i < n; i++)
+  {
+    ax[i].push_back(q[i]);
+    if (joint_type_of_input[i] != RDB_JOINT_REVOLUTE) continue;
+    for (double t = q[i] + two_pi; !(t > q_max[i]); t += two_pi) ax[i].push_back(t);  // while (true) { tmp += 2 pi; if (tmp > max) break; ... }
+    for (double t = q[i] - two_pi; !(t < q_min[i]); t -= two_pi) ax[i].push_back(t);
+  }
+  std::vector<std::vector<double>> all;
+  all.emplace_back(q, q + n);
+  for (int i = 0; i < n; i++)
+  {
+    const size_t have = all.size();
+    for (size_t is = 1; is < ax[i].size(); is++)
+      for (size_t im = 0; im < have; im++)
+      {
+        std::vector<double> v = all[im];
+        v[i] = ax[i][is];
+        all.push_back(std::move(v));
+      }
+  }
+  *count = (int64_t)all.size();
+  if (!out || capacity < *count) return RDB_ERR_INVALID_ARG;
+  for (size_t k = 0; k < all.size(); k++)
+    for (int i = 0; i < n; i++) out[k * (size_t)n + i] = all[k][i];
+  return RDB_OK;
+}

@@ -194,3 +194,40 @@ def test_gpu_ik_against_oracle(name):
     T = ch.kinematics(q, want=("T_tool",))["T_tool"]
     sol, stat, it, err = ch.computeLocalIk(T, q, qmin, qmax, toll=1e-9, max_iter=5)
     assert int(stat.sum()) == q.shape[1] and int(it.max()) == 0
+
+
+@pytest.mark.parametrize("name", ["c6", "random_b", "c7"])
+def test_multiplicity_against_reference(name):
+    """rdb_multiplicity (host-only entry, Chain::getMultiplicity PI.h:1470-1517) against the reference's own method in oracle/_ref: same
+    vectors in the same order, bit for bit."""
+    oracle = _oracle()
+    if not oracle.build_ref():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    from oracle.oracle import OracleChain
+    from rosdyn_b200.chain import multiplicity
+    d = fixtures.by_name(name)
+    rc = OracleChain(d, fast="ref")
+    types = [0] * d.n_inputs
+    for j in d.joints:
+        if j.input_index >= 0:
+            types[j.input_index] = int(j.type)
+    rng = np.random.RandomState(5)
+    dp = ctypes.POINTER(ctypes.c_double)
+    f = rc._l.lib.oracle_multiplicity
+    f.restype = ctypes.c_int64
+    f.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, ctypes.c_int64]
+    for trial in range(6):
+        q = rng.uniform(-1, 1, d.n_inputs)
+        qmin = -rng.uniform(0.5, 9.0, d.n_inputs)
+        qmax = rng.uniform(0.5, 9.0, d.n_inputs)
+        if trial == 0:
+            qmin[:], qmax[:] = -1.5, 1.5        # no extra turn fits: only q itself
+        ours = multiplicity(types, q, qmin, qmax)
+        cap = max(4096, ours.shape[0])
+        ref = np.zeros((cap, d.n_inputs))
+        cnt = f(rc._h, q.ctypes.data_as(dp), qmin.ctypes.data_as(dp), qmax.ctypes.data_as(dp), ref.ctypes.data_as(dp), cap)
+        assert cnt == ours.shape[0]
+        assert np.array_equal(ours, ref[:cnt])
+        if trial == 0:
+            assert cnt == 1
+        assert np.all(ours >= qmin - 1e-12) or trial != 0
