@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "launch.h"
@@ -69,6 +70,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
       "D:\n}" ::"r"(smem_u32(b)),
       "r"(parity)
       : "memory");
+}
+
+// compile-time loop: f(std::integral_constant<int, B>) ... f(std::integral_constant<int, E - 1>), so that indices derived from the loop
+// variable are constant expressions (accumulator arrays indexed through constexpr tables must stay in registers)
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+  if constexpr (B < E)
+  {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
 }
 
 // geometry of the augmented Gram matrix and of a slot for a (folded) chain of NJ joints, all of them inputs.
@@ -184,35 +197,48 @@ __device__ __forceinline__ void gen_load(const ChainDev<NJ>& C, const SamplesDev
 // REV: every joint of the (folded) chain is revolute -- the usual arm.  The joint type is then a compile-time fact: no type selects, the
 // linear half of every joint screw is an exact zero that is never multiplied, and the projection of a link on its own joint (unit twist
 // [0; axis] at birth) loses its linear terms.
-// component columns of the joint with angle q and rate dq (element-wise), zero padded to one tile.  A rolled loop in a real function,
-// called after the walk: the walk stays one basic block and no walker state has to survive the calls.
-__device__ __noinline__ void gram_component_columns(const int32_t* kind, const double* thr, const double* vmax, int nc, double q, double dq,
-                                                    double* __restrict__ o, int lane)
+// Component columns of every joint row (element-wise in q_j, Dq_j; zero padded to one tile), written after the walk by ONE rolled loop over
+// (joint, column): no call (a called function costs the walker its registers through the ABI -- it spilled 280 bytes per thread into an L1
+// that the slots leave at ~20 KB), little code, and the walk stays one basic block.  q_j / Dq_j are read again (L2 hits).
+template <int NJ>
+__device__ __forceinline__ void gram_component_columns(const ChainDev<NJ>& C, const GramComps& comps, const SamplesDev& in, int64_t i,
+                                                       double* __restrict__ slot, int lane)
 {
+  using G = GramGeom<NJ, 1>;
+  int base = 0;
 #pragma unroll 1
-  for (int c = 0; c < GX_COLS; c++)
+  for (int j = 0; j < NJ; j++)
   {
-    double val = 0.0;
-    if (c < nc)
+    const int len = G::P + 1 - 10 * j;  // regular columns of row j; the component columns follow
+    const int jin = C.joint[j].in, nc = comps.ncols[j];
+    const double q = ld_in(in.q, jin, in.ld, i), dq = ld_in(in.dq, jin, in.ld, i);
+    double* o = slot + base + len * 32;
+#pragma unroll 1
+    for (int c = 0; c < GX_COLS; c++)
     {
-      const int kd = kind[c];
-      const double th = thr[c], vm = vmax[c];
-      const double omega = fmin(fmax(dq, -vm), vm);
-      if (kd == GXK_OMEGA) val = omega;
-      else if (kd == GXK_Q) val = q;
-      else if (kd == GXK_ONE) val = 1.0;
-      else
+      double val = 0.0;
+      if (c < nc)
       {
-        const double r = omega / th;
-        if (kd == GXK_SAT) val = fmin(fmax(r, -1.0), 1.0);
+        const int kd = comps.kind[j][c];
+        const double th = comps.thr[j][c], vm = comps.vmax[j][c];
+        const double omega = fmin(fmax(dq, -vm), vm);
+        if (kd == GXK_OMEGA) val = omega;
+        else if (kd == GXK_Q) val = q;
+        else if (kd == GXK_ONE) val = 1.0;
         else
         {
-          const double sg = omega == 0.0 ? 0.0 : (omega > th ? 1.0 : (omega < -th ? -1.0 : r));
-          val = kd == GXK_SGN ? sg : omega * omega * sg;
+          const double r = omega / th;
+          if (kd == GXK_SAT) val = fmin(fmax(r, -1.0), 1.0);
+          else
+          {
+            const double sg = omega == 0.0 ? 0.0 : (omega > th ? 1.0 : (omega < -th ? -1.0 : r));
+            val = kd == GXK_SGN ? sg : omega * omega * sg;
+          }
         }
       }
+      o[c * 32 + (lane ^ (4 * (c & 3)))] = val;
     }
-    o[c * 32 + (lane ^ (4 * (c & 3)))] = val;
+    base += (len + GX_COLS) * 32;
   }
 }
 
@@ -317,14 +343,7 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramC
     const double tv = tau_meas ? __ldcs(tau_meas + (int64_t)C.joint[j].in * in.ld + i) : tau[j];
     slot[G::rowbase(j) + (P - 10 * j) * 32 + (lane ^ (4 * (P & 3)))] = tv;
   }
-  if (X)
-  {
-    // after the walk, when almost nothing is live across the calls; q_j / Dq_j are read again (L2 hits)
-#pragma unroll
-    for (int j = 0; j < NJ; j++)
-      gram_component_columns(comps.kind[j], comps.thr[j], comps.vmax[j], comps.ncols[j], ld_in(in.q, C.joint[j].in, in.ld, i),
-                             ld_in(in.dq, C.joint[j].in, in.ld, i), slot + G::rowbase(j) + (P + 1 - 10 * j) * 32, lane);
-  }
+  if (X) gram_component_columns<NJ>(C, comps, in, i, slot, lane);
 }
 
 // lanes past the end of the batch (last group only): their rows become exact zeros
@@ -477,13 +496,15 @@ template <int NJ, int PAR, int J>
 __device__ __forceinline__ void gram_cross_step(const double (&b)[GramGeom<NJ>::T], double bx, double (&acc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2])
 {
   using G = GramGeom<NJ, 1>;
-#pragma unroll
-  for (int I = 0; I < G::T; I++)
-  {
-    if (I < G::i0(J) || !G::xowns(J, I, GF_TS, PAR)) continue;
-    dmma884f(acc[G::xlocal(J, I, GF_TS, PAR)][0], acc[G::xlocal(J, I, GF_TS, PAR)][1], b[I], bx);
-  }
-  if (G::xowns(J, G::T, GF_TS, PAR)) dmma884f(acc[G::xlocal(J, G::T, GF_TS, PAR)][0], acc[G::xlocal(J, G::T, GF_TS, PAR)][1], bx, bx);
+  static_for<G::i0(J), G::T + 1>([&](auto Ic) {
+    constexpr int I = decltype(Ic)::value;
+    if constexpr (G::xowns(J, I, GF_TS, PAR))
+    {
+      constexpr int k = G::xlocal(J, I, GF_TS, PAR);
+      if constexpr (I < G::T) dmma884f(acc[k][0], acc[k][1], b[I], bx);
+      else dmma884f(acc[k][0], acc[k][1], bx, bx);  // (component, component) tile of joint J
+    }
+  });
 }
 template <int NJ, int PAR, int STEP>
 __device__ __forceinline__ void gram_cross_steps(const double* __restrict__ slot, int ks, int lane, const double (&bcur)[GramGeom<NJ>::T], double bxcur,
@@ -544,25 +565,27 @@ __device__ __forceinline__ void gram_cross_role(const SamplesDev& in, double* sm
   {
     if (ks == w)
     {
-#pragma unroll
-      for (int j = 0; j < NJ; j++)
-#pragma unroll
-        for (int I = 0; I <= G::T; I++)
-        {
-          if (I < G::i0(j) || !G::xowns(j, I, GF_TS, PAR)) continue;
-          double* o = smem + G::xtile(j, I) * 64 + g * 8 + 2 * t;
-          const int k = G::xlocal(j, I, GF_TS, PAR);
-          if (w == 0)
+      static_for<0, NJ>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        static_for<G::i0(j), G::T + 1>([&](auto Ic) {
+          constexpr int I = decltype(Ic)::value;
+          if constexpr (G::xowns(j, I, GF_TS, PAR))
           {
-            o[0] = acc[k][0];
-            o[1] = acc[k][1];
+            double* o = smem + G::xtile(j, I) * 64 + g * 8 + 2 * t;
+            constexpr int k = G::xlocal(j, I, GF_TS, PAR);
+            if (w == 0)
+            {
+              o[0] = acc[k][0];
+              o[1] = acc[k][1];
+            }
+            else
+            {
+              o[0] += acc[k][0];
+              o[1] += acc[k][1];
+            }
           }
-          else
-          {
-            o[0] += acc[k][0];
-            o[1] += acc[k][1];
-          }
-        }
+        });
+      });
     }
     bar_sync(GF_BAR_REDUCE, 32 * GF_MMA_WARPS);
   }
@@ -884,7 +907,8 @@ static cudaError_t launch_cross_nj(ChainHost& ch, const GramComps& gc, const Sam
   if (e != cudaSuccess) return e;
   const int64_t ngroups = (in.n + 31) / 32;
   const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + SLOTS - 1) / SLOTS);
-  gram_fused_kernel<NJ, SLOTS, REV, 1><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), gc, in, tau_meas, xpartial, 0);
+  static const int dbg = [] { const char* e = getenv("RDB_GRAM_DEBUG"); return e ? atoi(e) : 0; }();  // timing experiments only
+  gram_fused_kernel<NJ, SLOTS, REV, 1><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), gc, in, tau_meas, xpartial, dbg);
   count_launch();
   gram_cross_reduce_kernel<<<(G::NXT * 64 + 255) / 256, 256, 0, st>>>(xpartial, grid, G::NXT * 64, xsum);
   count_launch();
