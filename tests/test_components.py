@@ -89,8 +89,44 @@ def test_components_gpu_against_oracle():
     tau_meas = torch.tensor(tau_r + both - rigid.cpu().numpy(), device="cuda")                 # rigid + components
     G2, b2, _ = ch.regressorGramExt(q_, dq_, ddq_, tau_meas=tau_meas)
     assert_close(b2.cpu().numpy() / np.max(np.abs(b_ref)), np.einsum("ari,ri->a", X, tau_meas.cpu().numpy()) / np.max(np.abs(b_ref)), "rhs, measured torque", 1e-12)
+    # accumulation over two chunks == one pass; the matrix is symmetric; the general pipeline (RDB_GRAM_IMPL=v0 at load time) is the same
+    # computation, so its result is what the fused cross mode must reproduce on other chains too (folded chain with a massive tool below)
+    h = 2048
+    o = ch.regressorGramExt(q_[:, :h].contiguous(), dq_[:, :h].contiguous(), ddq_[:, :h].contiguous())
+    o = ch.regressorGramExt(q_[:, h:].contiguous(), dq_[:, h:].contiguous(), ddq_[:, h:].contiguous(), out=o)
+    assert float((o[0] - G).abs().max()) <= 1e-12 * float(G.abs().max()) and float((o[1] - b).abs().max()) <= 1e-12 * float(b.abs().max())
+    assert bool((G == G.T).all())
     # the rigid-body entry is unchanged by the components
     G0, _, _ = ch.regressorGram(q_, dq_, ddq_)
     assert_close(G0.cpu().numpy() / np.max(np.abs(G_ref)), G_ref[:70, :70] / np.max(np.abs(G_ref)), "rigid gram", 1e-12)
     ch.setComponents([])
     assert ch.getComponentColumns() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c6_perturbed", "c7_perturbed", "random_b"])
+def test_extended_gram_on_folded_and_mixed_chains(name):
+    """Cross mode of the fused kernel on chains with a massive rigidly attached link, 7 moving joints, prismatic joints: the extended normal
+    equations against the oracle's regressor and component columns contracted in numpy."""
+    import torch
+    from oracle.oracle import OracleChain
+    from rosdyn_b200.chain import Chain
+    d = fixtures.by_name(name)
+    ch, oc = Chain(d), OracleChain(d)
+    n_in = d.n_inputs
+    comps = [(1 + (k % 3), k % n_in, 0.05, 0.7) for k in range(n_in + 2)]   # two joints carry two components
+    tn = {1: "friction1", 2: "friction2", 3: "spring"}
+    pc = ch.setComponents([{"type": tn[t], "joint": j, "min_velocity": lo, "max_velocity": hi} for t, j, lo, hi in comps])
+    n = 3000
+    rng = np.random.RandomState(4)
+    q, dq, ddq = (rng.uniform(-1, 1, (n_in, n)) for _ in range(3))
+    phi, tau_r = oc.regressor_torque(q, dq, ddq)
+    ref_c = oracle.components_regressor(comps, n_in, q, dq)
+    P = 10 * d.n_joints
+    X = np.concatenate([phi.reshape(P, n_in, n), ref_c.reshape(pc, n_in, n)], axis=0)
+    G_ref = np.einsum("ari,bri->ab", X, X)
+    b_ref = np.einsum("ari,ri->a", X, tau_r)
+    G, b, tt = ch.regressorGramExt(*(torch.tensor(x, device="cuda") for x in (q, dq, ddq)))
+    assert_close(G.cpu().numpy() / np.max(np.abs(G_ref)), G_ref / np.max(np.abs(G_ref)), "extended gram", 1e-11)
+    assert_close(b.cpu().numpy() / np.max(np.abs(b_ref)), b_ref / np.max(np.abs(b_ref)), "extended rhs", 1e-11)
+    assert bool((G == G.T).all())
