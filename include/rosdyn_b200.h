@@ -248,7 +248,8 @@ rdb_status rdb_regressor_gram_ext_batch(const rdb_chain* chain, const rdb_sample
 /* Chain::getMultiplicity (PI.h:1470-1517), HOST arrays: every joint vector q + 2 pi k that stays inside [q_min, q_max], revolute input
  * joints only (joint_type_of_input[i] = RDB_JOINT_* of the chain joint fed by input i), in the reference's order (q first; per joint
  * the positive turns, then the negative ones; joints combined base -> tool).  out[count][n_inputs] row-major; *count is always set to the
- * number of vectors; RDB_ERR_INVALID_ARG when capacity is too small (nothing beyond capacity is written). */
+ * number of vectors; RDB_ERR_INVALID_ARG when capacity is too small (nothing beyond capacity is written) or when a revolute joint's limits
+ * span more than 1000 turns (the reference would enumerate them all). */
 rdb_status rdb_multiplicity(int32_t n_inputs, const int32_t* joint_type_of_input, const double* q, const double* q_min, const double* q_max,
                             double* out, int64_t capacity, int64_t* count);
 

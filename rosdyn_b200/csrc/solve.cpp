@@ -112,6 +112,10 @@ extern "C" rdb_status rdb_multiplicity(int32_t n, const int32_t* joint_type_of_i
 {
   if (n < 0 || !count || (n > 0 && (!joint_type_of_input || !q || !q_min || !q_max))) return RDB_ERR_INVALID_ARG;
   const double two_pi = 2.0 * 3.14159265358979323846;  // 2*M_PI
+  // the reference loops until the limit is passed; with its "no limit" defaults (+-1e10, PI.h:92-93) that is 1.6e9 turns per joint and an
+  // exponential number of vectors -- refuse limits wider than 10^3 turns instead of reproducing that
+  for (int i = 0; i < n; i++)
+    if (joint_type_of_input[i] == RDB_JOINT_REVOLUTE && !((q_max[i] - q_min[i]) <= 1.0e3 * two_pi)) return RDB_ERR_INVALID_ARG;
   std::vector<std::vector<double>> ax((size_t)n);
   for (int i = 0; i < n; i++)
   {
