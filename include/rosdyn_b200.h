@@ -261,6 +261,17 @@ rdb_status rdb_multiplicity(int32_t n_inputs, const int32_t* joint_type_of_input
 rdb_status rdb_normal_equations_solve(int32_t P, const double* gram, const double* rhs, double tau_sq, double rel_tol, double* parameters,
                                       double* eigenvalues, int32_t* rank, double* residual_sq);
 
+/* ---- one process, several GPUs ---------------------------------------------------------------
+ * rdb_chain_create uses the CURRENT device; rdb_chain_create_on creates the handle on `device` (and restores the current device).
+ * rdb_regressor_gram_sharded_host: samples are independent, so the HOST batch is cut into n_chains contiguous shards
+ * [r n / R, (r+1) n / R), shard r runs through rdb_regressor_gram_batch_host on chains[r] (its device; one worker thread per handle, all
+ * concurrently), and the R partial normal equations are summed on the host in rank order -- bit-reproducible for a given R, no collective
+ * library needed.  The handles must describe the same chain (same joints / inputs); several handles may share a device. */
+rdb_status rdb_chain_create_on(const rdb_chain_desc* desc, int32_t device, rdb_chain** out);
+int32_t rdb_chain_device(const rdb_chain* chain);
+rdb_status rdb_regressor_gram_sharded_host(rdb_chain* const* chains, int32_t n_chains, const rdb_samples* in, const double* tau_meas,
+                                           double* gram, double* rhs, double* tau_sq, int32_t accumulate);
+
 /* ---- host-buffer convenience wrappers (pointers are HOST pointers; copies + sync inside) ---------- */
 rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out);
 rdb_status rdb_torque_batch_host(const rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out);

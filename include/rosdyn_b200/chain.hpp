@@ -206,6 +206,15 @@ public:
   {
     check(rdb_local_ik_batch(m_h, n, ld, target, seed, q_min, q_max, weight, toll, max_iter, sol, status, iterations, error_norm, stream));
   }
+  // one process, several GPUs: contiguous shards of a HOST batch on the given chains (one per device, see rdb_chain_create_on), partial
+  // normal equations summed on the host in rank order
+  static void regressorGramSharded(const std::vector<Chain*>& chains, const rdb_samples& in, const double* tau_meas, double* gram, double* rhs,
+                                   double* tau_sq, bool accumulate = false)
+  {
+    std::vector<rdb_chain*> h;
+    for (Chain* c : chains) h.push_back(c->m_h);
+    check(rdb_regressor_gram_sharded_host(h.data(), (int32_t)h.size(), &in, tau_meas, gram, rhs, tau_sq, accumulate ? 1 : 0));
+  }
   // Chain::getMultiplicity (primitives_impl.h:1470-1517): multi-turn images of q inside [q_min, q_max]; joint_type_of_input[i] = RDB_JOINT_*
   static std::vector<std::vector<double>> getMultiplicity(const std::vector<int32_t>& joint_type_of_input, const std::vector<double>& q,
                                                           const std::vector<double>& q_min, const std::vector<double>& q_max)

@@ -42,12 +42,16 @@ def _is_torch(x) -> bool:
 class Chain:
     """Batched B200 drop-in for rosdyn::Chain (hot path only: kinematics, twists, RNEA, regressor, inertia)."""
 
-    def __init__(self, desc: ChainDesc):
+    def __init__(self, desc: ChainDesc, device: Optional[int] = None):
+        """device: CUDA device index of the handle (None = the current device, as rdb_chain_create)."""
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         self.desc = desc
         cdesc, keep = to_ctypes(desc)
-        check(self._lib.rdb_chain_create(ctypes.byref(cdesc), ctypes.byref(self._h)))
+        if device is None:
+            check(self._lib.rdb_chain_create(ctypes.byref(cdesc), ctypes.byref(self._h)))
+        else:
+            check(self._lib.rdb_chain_create_on(ctypes.byref(cdesc), int(device), ctypes.byref(self._h)))
         del keep
         self.nJ = self._lib.rdb_chain_joints_number(self._h)
         self.nL = self._lib.rdb_chain_links_number(self._h)

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "launch.h"
@@ -499,6 +500,60 @@ rdb_status rdb_fp64_peak(int32_t kind, int32_t reps, double* tflops)
   if (!tflops || kind < 0 || kind > 2) return fail(RDB_ERR_INVALID_ARG, "fp64_peak: bad argument");
   if (rdb_device_count() <= 0) return fail(RDB_ERR_NO_DEVICE, "no CUDA device");
   RDB_CUDA(fp64_peak(kind, reps, tflops));
+  return RDB_OK;
+}
+
+rdb_status rdb_chain_create_on(const rdb_chain_desc* desc, int32_t device, rdb_chain** out)
+{
+  int cur = 0;
+  if (rdb_device_count() <= 0) return fail(RDB_ERR_NO_DEVICE, "no CUDA device: rosdyn_b200 has no CPU fallback");
+  RDB_CUDA(cudaGetDevice(&cur));
+  RDB_CUDA(cudaSetDevice(device));
+  const rdb_status s = rdb_chain_create(desc, out);
+  cudaSetDevice(cur);
+  return s;
+}
+
+int32_t rdb_chain_device(const rdb_chain* chain) { return chain ? chain->device : -1; }
+
+rdb_status rdb_regressor_gram_sharded_host(rdb_chain* const* chains, int32_t n_chains, const rdb_samples* in, const double* tau_meas,
+                                           double* gram, double* rhs, double* tau_sq, int32_t accumulate)
+{
+  if (!chains || n_chains <= 0 || !in) return fail(RDB_ERR_INVALID_ARG, "null chains or samples");
+  for (int r = 0; r < n_chains; r++)
+    if (!chains[r] || chains[r]->host.nj != chains[0]->host.nj || chains[r]->host.n_in != chains[0]->host.n_in)
+      return fail(RDB_ERR_INVALID_ARG, "the handles must describe the same chain");
+  {
+    const rdb_status cs = check_samples(chains[0], in, true);
+    if (cs != RDB_OK) return cs;
+  }
+  if (!gram || !rhs) return fail(RDB_ERR_INVALID_ARG, "gram / rhs must not be null");
+  const int R = n_chains, P = 10 * chains[0]->host.nj;
+  const size_t n_out = (size_t)P * P + P + 1;
+  std::vector<double> part((size_t)R * n_out, 0.0);
+  std::vector<rdb_status> st((size_t)R, RDB_OK);
+  std::vector<std::string> msg((size_t)R);
+  std::vector<std::thread> th;
+  for (int r = 0; r < R; r++)
+    th.emplace_back([&, r] {
+      cudaSetDevice(chains[r]->device);
+      const int64_t lo = (int64_t)r * in->n / R, hi = (int64_t)(r + 1) * in->n / R;
+      rdb_samples v{hi - lo, in->ld, in->q ? in->q + lo : nullptr, in->dq ? in->dq + lo : nullptr, in->ddq ? in->ddq + lo : nullptr, nullptr};
+      double* o = part.data() + (size_t)r * n_out;
+      st[r] = rdb_regressor_gram_batch_host(chains[r], &v, tau_meas ? tau_meas + lo : nullptr, o, o + (size_t)P * P, o + (size_t)P * P + P, 0);
+      if (st[r] != RDB_OK) msg[r] = rdb_last_error();  // thread-local text of this worker
+    });
+  for (auto& t : th) t.join();
+  for (int r = 0; r < R; r++)
+    if (st[r] != RDB_OK) return fail(st[r], "shard " + std::to_string(r) + ": " + msg[r]);
+  for (size_t e = 0; e < n_out; e++)
+  {
+    double* dst = e < (size_t)P * P ? gram + e : (e < (size_t)P * P + P ? rhs + (e - (size_t)P * P) : tau_sq);
+    if (!dst) continue;
+    double s = accumulate ? *dst : 0.0;
+    for (int r = 0; r < R; r++) s += part[(size_t)r * n_out + e];  // rank order: reproducible for a given R
+    *dst = s;
+  }
   return RDB_OK;
 }
 

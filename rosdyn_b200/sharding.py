@@ -37,3 +37,25 @@ def allreduce_normal_equations(G, b, tau_sq, group=None, flat=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return unpack_normal_equations(flat, P)
+
+
+def sharded_gram_host(chains, q, dq, ddq, tau_meas=None):
+    """One process, several handles / GPUs (rdb_regressor_gram_sharded_host): the HOST batch q/dq/ddq [n_act][N] (numpy, ideally pinned)
+    is cut into len(chains) contiguous shards, every handle runs its shard through its own host pipeline concurrently, and the partial
+    normal equations are summed on the host in rank order.  Returns (G[P,P], b[P], tau_sq) as numpy."""
+    import ctypes
+
+    import numpy as np
+
+    from ._lib import CSamples, check, load
+    lib = load()
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (q, dq, ddq)]
+    n_in, n = arrs[0].shape
+    tm = None if tau_meas is None else np.ascontiguousarray(tau_meas, dtype=np.float64)
+    P = 10 * chains[0].nJ
+    G, b, tt = np.zeros((P, P)), np.zeros(P), np.zeros(1)
+    hs = (ctypes.c_void_p * len(chains))(*[c._h for c in chains])
+    vp = lambda a: None if a is None else ctypes.c_void_p(a.ctypes.data)  # noqa: E731
+    s = CSamples(n, n, vp(arrs[0]), vp(arrs[1]), vp(arrs[2]), None)
+    check(lib.rdb_regressor_gram_sharded_host(hs, len(chains), ctypes.byref(s), vp(tm), vp(G), vp(b), vp(tt), 0))
+    return G, b, float(tt[0])

@@ -297,6 +297,30 @@ def test_gram_large_batch_invariants(chains, torch):
         del phi, F
 
 
+def test_sharded_gram_single_process(chains, torch):
+    """rdb_regressor_gram_sharded_host: several handles (one per GPU when the box has more than one, else all on cuda:0) each take a
+    contiguous shard of a host batch; the rank-ordered host sum equals the single-handle result and the oracle."""
+    from rosdyn_b200.chain import Chain
+    from rosdyn_b200.sharding import sharded_gram_host
+    d, ch, oc = chains("c6")
+    ndev = torch.cuda.device_count()
+    handles = [Chain(d, device=r % ndev) for r in range(3)]
+    assert [h._lib.rdb_chain_device(h._h) for h in handles] == [r % ndev for r in range(3)]
+    n = 300_001
+    q, dq, ddq, _ = (_np(x) for x in _inputs(torch, 6, n, 0x5EED0003))
+    G, b, tt = sharded_gram_host(handles, q, dq, ddq)
+    G1, b1, t1 = (_np(x) for x in ch.regressorGram(*(torch.tensor(x, device="cuda") for x in (q, dq, ddq))))
+    scale = np.max(np.abs(G1))
+    assert np.max(np.abs(G - G1)) <= 1e-12 * scale and np.max(np.abs(b - b1)) <= 1e-12 * np.max(np.abs(b1))
+    assert abs(tt - t1[0]) <= 1e-12 * t1[0]
+    G2, b2, _ = sharded_gram_host(handles, q, dq, ddq)
+    assert np.array_equal(G, G2) and np.array_equal(b, b2)          # rank-ordered host sum: reproducible
+    m = 20_000
+    Gr, br, _ = oc.gram(q[:, :m], dq[:, :m], ddq[:, :m])
+    Gs, bs, _ = sharded_gram_host(handles[:2], q[:, :m].copy(), dq[:, :m].copy(), ddq[:, :m].copy())
+    assert np.max(np.abs(Gs - Gr)) <= 1e-10 * np.max(np.abs(Gr)) and np.max(np.abs(bs - br)) <= 1e-10 * np.max(np.abs(br))
+
+
 def test_chain_from_urdf(chains, torch):
     """createChain(urdf, base, tool, g) through the library's URDF loader == the hand-written fixture chain."""
     import os
