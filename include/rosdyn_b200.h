@@ -253,6 +253,12 @@ rdb_status rdb_regressor_gram_ext_batch(const rdb_chain* chain, const rdb_sample
 rdb_status rdb_multiplicity(int32_t n_inputs, const int32_t* joint_type_of_input, const double* q, const double* q_min, const double* q_max,
                             double* out, int64_t capacity, int64_t* count);
 
+/* Host-only utility (used by the tests): the constant 10x10 map T = d(parameters referred to frame A) / d(parameters referred to frame B)
+ * of a body rigidly attached with x_A = R x_B + t (R row-major), T[c * 10 + p], parameters [m, m c, Ixx, Ixy, Ixz, Iyy, Iyz, Izz] about
+ * the frame origin (PI.h:399-417).  It is what folds never-moving joints out of the chain for the fused normal equations, the torque and
+ * the inertia walkers: Phi[:, block B] = Phi[:, block A] T. */
+rdb_status rdb_fold_parameter_map(const double* R, const double* t, double* T);
+
 /* ---- normal-equation solve (HOST arrays, no reference code: the consumer is external) ------
  * Minimum-norm least-squares solution of gram * parameters = rhs through a symmetric eigen-decomposition: the regressor is rank
  * deficient in the standard parameters, so eigenvalues <= rel_tol * lambda_max (rel_tol <= 0: 1e-10) are discarded.

@@ -60,6 +60,20 @@ static void fold_param_map(const FoldXf& X, double* T)
   }
 }
 
+}  // namespace rdb
+// host-only entry for tests: the parameter map of a rigid attachment x_A = R x_B + t (row-major R), T[c * 10 + p]
+extern "C" rdb_status rdb_fold_parameter_map(const double* R, const double* t, double* T)
+{
+  if (!R || !t || !T) return RDB_ERR_INVALID_ARG;
+  rdb::FoldXf X;
+  for (int k = 0; k < 9; k++) X.R[k] = R[k];
+  for (int k = 0; k < 3; k++) X.t[k] = t[k];
+  rdb::fold_param_map(X, T);
+  return RDB_OK;
+}
+namespace rdb
+{
+
 // (re)builds ch.gram.fold* for the current model (called by every model upload, capi.cu)
 cudaError_t fold_chain(ChainHost& ch)
 {
