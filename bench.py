@@ -380,8 +380,8 @@ def main():
         # fold_chain), and of the (P'+1)x(P'+1) augmented Gram matrix only the upper-triangular 8x8 tiles right of each row's first
         # non-zero column are multiplied (one DMMA m8n8k4 = 512 flop per tile per 4 samples)
         K = sum(1 for j in d.joints if j.input_index >= 0)
-        T = (10 * K + 1 + 7) // 8
-        dmma4 = sum((T - (10 * j) // 8) * (T - (10 * j) // 8 + 1) // 2 for j in range(K))
+        # the row of joint j spans the first ceil((1 + 10 (K - j)) / 8) tiles (the kernel orders the columns tau, last link ... first link)
+        dmma4 = sum(((1 + 10 * (K - j) + 7) // 8) * ((1 + 10 * (K - j) + 7) // 8 + 1) // 2 for j in range(K))
         ex = dmma4 * 512 / 4
         sps = S / (ms * 1e-3 / args.steps)
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None,

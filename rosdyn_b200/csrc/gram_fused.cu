@@ -9,8 +9,8 @@
 //     non-zero columns, XOR-swizzled, conflict free).  The inputs of the next group are requested BEFORE waiting for the slot, so the DRAM
 //     latency hides behind the consumers; sin/cos of all joints are evaluated up front (branch free), so the walk is one basic block.
 //   * MMA warps: consume a slot as soon as it is full.  The contraction index k = (sample, joint row); a k-step is 4 samples of one joint
-//     row, so the zero pattern of Phi (row of chain joint j is zero left of column 10 j) is known at compile time and whole 8x8 tiles are
-//     skipped.  The upper-triangular tiles of the (P+1)x(P+1) augmented Gram matrix stay in registers for the whole kernel; the four SM
+//     row, so the zero pattern of Phi (row of chain joint j is zero in the blocks of the links before j) is known at compile time and whole
+//     8x8 tiles are skipped; inside the kernel the columns run tau, last link ... first link, so that every row is a PREFIX of tiles.  The upper-triangular tiles of the (P+1)x(P+1) augmented Gram matrix stay in registers for the whole kernel; the four SM
 //     sub-partitions split the k-steps of a slot, GF_TSPLIT warps per sub-partition split the tile rows by parity.  The k-steps of a slot
 //     are fully unrolled and software pipelined: the fragments of step n+1 are loaded while the DMMAs of step n issue.
 //     tcgen05 has no f64 kind: the FP64 tensor path of sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA).
@@ -96,7 +96,7 @@ struct GramGeom
   static constexpr int KPW = 8 / GF_KSPLIT;   // k-steps (4 samples) of one MMA warp per joint row and slot
   static constexpr int NSTEPS = NJ * KPW;     // k-steps of one MMA warp per slot
   __host__ __device__ static constexpr int threads(int slots) { return 32 * (GF_MMA_WARPS + slots); }
-  // offset (doubles) of the row of joint j inside a slot: [column - 10 j][sample], only the columns 10 j .. P (tau) are stored
+  // offset (doubles) of the row of joint j inside a slot: [position][sample], only the positions 0 .. rowlen(j)-1 are stored
   __host__ __device__ static constexpr int rowbase(int j)
   {
     int o = 0;
@@ -121,27 +121,33 @@ struct GramGeom
       if (owns(K, ts, par)) n += T - K;
     return n + (J - I);
   }
-  // cross mode: per joint row j the tiles (regular tile I, component tile of joint j), I = I0(j) .. T-1, then (component, component)
-  __host__ __device__ static constexpr int i0(int j) { return (10 * j) / 8; }
-  __host__ __device__ static constexpr int xtile(int j, int I)  // I == T: the (component, component) tile
+  // Column order inside the kernel: POSITION 0 is tau, then the link blocks from the LAST link to the first (position of column 10 l + p:
+  // 1 + 10 (NJ-1-l) + p).  The row of joint j is non-zero in the blocks of the links >= j, i.e. in the positions [0, rowlen(j)) -- a prefix,
+  // aligned with the 8-wide tiles at its start, ragged only at its end: row j needs the tiles I, K < tj(j) (C6: 104 DMMA per 4 samples;
+  // with the natural order, where a row starts at column 10 j in the middle of a tile, it was 109).
+  __host__ __device__ static constexpr int pos(int l, int p) { return 1 + 10 * (NJ - 1 - l) + p; }
+  __host__ __device__ static constexpr int rowlen(int j) { return 1 + 10 * (NJ - j); }
+  __host__ __device__ static constexpr int tj(int j) { return (rowlen(j) + 7) / 8; }
+  // cross mode: per joint row j the tiles (regular tile I, component tile of joint j), I = 0 .. tj(j)-1, then (component, component)
+  __host__ __device__ static constexpr int xtile(int j, int I)  // I == tj(j): the (component, component) tile
   {
     int n = 0;
-    for (int k = 0; k < j; k++) n += T - i0(k) + 1;
-    return n + (I - i0(j));
+    for (int k = 0; k < j; k++) n += tj(k) + 1;
+    return n + I;
   }
   __host__ __device__ static constexpr int nxt()
   {
     int n = 0;
-    for (int k = 0; k < NJ; k++) n += T - i0(k) + 1;
+    for (int k = 0; k < NJ; k++) n += tj(k) + 1;
     return n;
   }
   static constexpr int NXT = nxt();
-  __host__ __device__ static constexpr bool xowns(int j, int I, int ts, int par) { return ts == 1 || ((I == T ? j : I) & 1) == par; }
+  __host__ __device__ static constexpr bool xowns(int j, int I, int ts, int par) { return ts == 1 || ((I == tj(j) ? j : I) & 1) == par; }
   __host__ __device__ static constexpr int xlocal(int j, int I, int ts, int par)
   {
     int n = 0;
     for (int k = 0; k <= j; k++)
-      for (int K = i0(k); K <= T; K++)
+      for (int K = 0; K <= tj(k); K++)
       {
         if (k == j && K == I) return n;
         if (xowns(k, K, ts, par)) n++;
@@ -152,7 +158,7 @@ struct GramGeom
   {
     int n = 0;
     for (int k = 0; k < NJ; k++)
-      for (int K = i0(k); K <= T; K++)
+      for (int K = 0; K <= tj(k); K++)
         if (xowns(k, K, ts, par)) n++;
     return n;
   }
@@ -209,7 +215,7 @@ __device__ __forceinline__ void gram_component_columns(const ChainDev<NJ>& C, co
 #pragma unroll 1
   for (int j = 0; j < NJ; j++)
   {
-    const int len = G::P + 1 - 10 * j;  // regular columns of row j; the component columns follow
+    const int len = 1 + 10 * (NJ - j);  // rowlen(j): regular positions of row j; the component columns follow
     const int jin = C.joint[j].in, nc = comps.ncols[j];
     const double q = ld_in(in.q, jin, in.ld, i), dq = ld_in(in.dq, jin, in.ld, i);
     double* o = slot + base + len * 32;
@@ -332,16 +338,16 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramC
 #pragma unroll
       for (int p = 3; p < 10; p += 2) t1 = fma(e[p], Pl[p], t1);
       tau[j] = t0 + t1;
-      double* o = slot + G::rowbase(j) + (10 * (l - j)) * 32;
+      double* o = slot + G::rowbase(j) + G::pos(l, 0) * 32;
 #pragma unroll
-      for (int p = 0; p < 10; p++) o[p * 32 + (lane ^ (4 * ((10 * l + p) & 3)))] = e[p];
+      for (int p = 0; p < 10; p++) o[p * 32 + (lane ^ (4 * (G::pos(l, p) & 3)))] = e[p];
     }
   }
 #pragma unroll
   for (int j = 0; j < NJ; j++)
   {
     const double tv = tau_meas ? __ldcs(tau_meas + (int64_t)C.joint[j].in * in.ld + i) : tau[j];
-    slot[G::rowbase(j) + (P - 10 * j) * 32 + (lane ^ (4 * (P & 3)))] = tv;
+    slot[G::rowbase(j) + lane] = tv;  // position 0
   }
   if (X) gram_component_columns<NJ>(C, comps, in, i, slot, lane);
 }
@@ -353,9 +359,9 @@ __device__ __noinline__ void gram_zero_lane(double* __restrict__ slot, int lane)
   using G = GramGeom<NJ, X>;
   for (int j = 0; j < NJ; j++)
   {
-    for (int c = 10 * j; c <= G::P; c++) slot[G::rowbase(j) + (c - 10 * j) * 32 + (lane ^ (4 * (c & 3)))] = 0.0;
+    for (int c = 0; c < G::rowlen(j); c++) slot[G::rowbase(j) + c * 32 + (lane ^ (4 * (c & 3)))] = 0.0;
     if (X)
-      for (int c = 0; c < GX_COLS; c++) slot[G::rowbase(j) + (G::P + 1 - 10 * j + c) * 32 + (lane ^ (4 * (c & 3)))] = 0.0;
+      for (int c = 0; c < GX_COLS; c++) slot[G::rowbase(j) + (G::rowlen(j) + c) * 32 + (lane ^ (4 * (c & 3)))] = 0.0;
   }
 }
 
@@ -365,16 +371,15 @@ template <int NJ, int J, int X = 0>
 __device__ __forceinline__ void gram_load_frags(const double* __restrict__ slot, int kk, int lane, double (&b)[GramGeom<NJ>::T])
 {
   using G = GramGeom<NJ, X>;
-  constexpr int P = G::P, T = G::T, c0 = 10 * J, I0 = c0 / 8;
+  constexpr int T = G::T, L = G::rowlen(J), TJ = G::tj(J);
   const int g = lane >> 2, t = lane & 3;
   const double* rowp = slot + G::rowbase(J) + ((4 * kk + t) ^ (4 * (g & 3)));
 #pragma unroll
   for (int I = 0; I < T; I++)
   {
-    if (I < I0) continue;
+    if (I >= TJ) continue;
     const int col = 8 * I + g;
-    const bool all_valid = (8 * I >= c0) && (8 * I + 7 <= P);
-    if (all_valid || (col >= c0 && col <= P)) b[I] = rowp[(col - c0) * 32];
+    if (8 * I + 7 < L || col < L) b[I] = rowp[col * 32];  // only the last tile of the row can be ragged
     else b[I] = 0.0;
   }
 }
@@ -382,13 +387,14 @@ template <int NJ, int PAR, int J>
 __device__ __forceinline__ void gram_mma_step(const double (&b)[GramGeom<NJ>::T], double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
 {
   using G = GramGeom<NJ>;
-  constexpr int T = G::T, I0 = (10 * J) / 8;
+  constexpr int T = G::T, TJ = G::tj(J);
 #pragma unroll
   for (int I = 0; I < T; I++)
   {
-    if (I < I0 || !G::owns(I, GF_TS, PAR)) continue;
+    if (I >= TJ || !G::owns(I, GF_TS, PAR)) continue;
 #pragma unroll
-    for (int K = I; K < T; K++) dmma884f(acc[G::local(I, K, GF_TS, PAR)][0], acc[G::local(I, K, GF_TS, PAR)][1], b[I], b[K]);
+    for (int K = I; K < T; K++)
+      if (K < TJ) dmma884f(acc[G::local(I, K, GF_TS, PAR)][0], acc[G::local(I, K, GF_TS, PAR)][1], b[I], b[K]);
   }
 }
 // k-steps STEP.. of this warp in one slot; step = (joint row, k-step of the warp); the fragments of the next step are in flight while the
@@ -490,18 +496,18 @@ __device__ __forceinline__ double gram_load_xfrag(const double* __restrict__ slo
 {
   using G = GramGeom<NJ, 1>;
   const int g = lane >> 2, t = lane & 3;
-  return slot[G::rowbase(J) + (G::P + 1 - 10 * J + g) * 32 + ((4 * kk + t) ^ (4 * (g & 3)))];
+  return slot[G::rowbase(J) + (G::rowlen(J) + g) * 32 + ((4 * kk + t) ^ (4 * (g & 3)))];
 }
 template <int NJ, int PAR, int J>
 __device__ __forceinline__ void gram_cross_step(const double (&b)[GramGeom<NJ>::T], double bx, double (&acc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2])
 {
   using G = GramGeom<NJ, 1>;
-  static_for<G::i0(J), G::T + 1>([&](auto Ic) {
+  static_for<0, G::tj(J) + 1>([&](auto Ic) {
     constexpr int I = decltype(Ic)::value;
     if constexpr (G::xowns(J, I, GF_TS, PAR))
     {
       constexpr int k = G::xlocal(J, I, GF_TS, PAR);
-      if constexpr (I < G::T) dmma884f(acc[k][0], acc[k][1], b[I], bx);
+      if constexpr (I < G::tj(J)) dmma884f(acc[k][0], acc[k][1], b[I], bx);
       else dmma884f(acc[k][0], acc[k][1], bx, bx);  // (component, component) tile of joint J
     }
   });
@@ -567,7 +573,7 @@ __device__ __forceinline__ void gram_cross_role(const SamplesDev& in, double* sm
     {
       static_for<0, NJ>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
-        static_for<G::i0(j), G::T + 1>([&](auto Ic) {
+        static_for<0, G::tj(j) + 1>([&](auto Ic) {
           constexpr int I = decltype(Ic)::value;
           if constexpr (G::xowns(j, I, GF_TS, PAR))
           {
@@ -677,17 +683,24 @@ __global__ void gram_fused_reduce_kernel(const double* __restrict__ partial, int
     I++;
   }
   const int J = I + k;
-  const int row = 8 * I + ((e >> 3) & 7), col = 8 * J + (e & 7);
-  if (row > P || col > P) return;
-  if (I == J && row > col) return;
-  if (col < P)
+  const int rp = 8 * I + ((e >> 3) & 7), cp = 8 * J + (e & 7);  // positions inside the kernel (GramGeom::pos)
+  if (rp > P || cp > P) return;
+  if (I == J && rp > cp) return;  // diagonal tiles hold both halves; keep the upper one
+  // position -> column of the (folded) parameter vector, P = tau
+  const int nj = P / 10;
+  const int row = rp == 0 ? P : 10 * (nj - 1 - (rp - 1) / 10) + (rp - 1) % 10;
+  const int col = cp == 0 ? P : 10 * (nj - 1 - (cp - 1) / 10) + (cp - 1) % 10;
+  if (row < P && col < P)
   {
     const double v = accumulate ? gram[(size_t)col * P + row] + s : s;
     gram[(size_t)col * P + row] = v;
     if (row != col) gram[(size_t)row * P + col] = v;
   }
-  else if (row < P)
-    rhs[row] = accumulate ? rhs[row] + s : s;
+  else if (row < P || col < P)
+  {
+    const int a = row < P ? row : col;
+    rhs[a] = accumulate ? rhs[a] + s : s;
+  }
   else if (tau_sq)
     *tau_sq = accumulate ? *tau_sq + s : s;
 }
@@ -855,17 +868,19 @@ __global__ void gram_cross_finish_kernel(const double* __restrict__ X, const dou
                                          const int32_t* __restrict__ xj, const int32_t* __restrict__ xs, int nj, int njr, int Pc,
                                          double* __restrict__ gram, double* __restrict__ rhs, int accumulate)
 {
-  const int P = 10 * nj, Pr = 10 * njr, Pt = P + Pc, T = (Pr + 1 + 7) / 8;
+  const int P = 10 * nj, Pr = 10 * njr, Pt = P + Pc;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (P + 1 + Pc) * Pc) return;
   const int a = e / Pc, cc = e % Pc;
   const int j = xj[cc], g = xs[cc];
+  auto tjf = [&](int k) { return (1 + 10 * (njr - k) + 7) / 8; };  // GramGeom::tj
   int tb = 0;  // first cross tile of joint j
-  for (int k = 0; k < j; k++) tb += T - (10 * k) / 8 + 1;
-  const int i0 = (10 * j) / 8;
-  auto xval = [&](int col) -> double {  // reduced regular column `col` (<= Pr) against (j, g)
-    const int I = col >> 3;
-    return I < i0 ? 0.0 : X[(size_t)(tb + I - i0) * 64 + (col & 7) * 8 + g];
+  for (int k = 0; k < j; k++) tb += tjf(k) + 1;
+  const int tjj = tjf(j);
+  auto xval = [&](int col) -> double {  // reduced regular column `col` (Pr = tau) against (j, g)
+    const int pos = col == Pr ? 0 : 1 + 10 * (njr - 1 - col / 10) + col % 10;  // GramGeom::pos
+    const int I = pos >> 3;
+    return (pos >= 1 + 10 * (njr - j)) ? 0.0 : X[(size_t)(tb + I) * 64 + (pos & 7) * 8 + g];
   };
   if (a < P)
   {
@@ -891,7 +906,7 @@ __global__ void gram_cross_finish_kernel(const double* __restrict__ X, const dou
   else
   {
     const int c2 = a - P - 1;
-    const double s = (xj[c2] == j) ? X[(size_t)(tb + T - i0) * 64 + xs[c2] * 8 + g] : 0.0;
+    const double s = (xj[c2] == j) ? X[(size_t)(tb + tjj) * 64 + xs[c2] * 8 + g] : 0.0;
     double* o = gram + (size_t)(P + cc) * Pt + P + c2;
     *o = accumulate ? *o + s : s;
   }
@@ -948,9 +963,8 @@ cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const dou
   }
   bool rev = true;
   for (int j = 0; j < K; j++) rev = rev && F.joint[j].type == RDB_JOINT_REVOLUTE;
-  const int T = (10 * K + 1 + 7) / 8;
   int nxt = 0;
-  for (int j = 0; j < K; j++) nxt += T - (10 * j) / 8 + 1;
+  for (int j = 0; j < K; j++) nxt += (1 + 10 * (K - j) + 7) / 8 + 1;  // GramGeom::nxt
   // workspace: rigid block (P*P + P + 1) | cross sums (nxt*64) | cross partials (sm_count*nxt*64) | component map (2 Pc ints)
   const size_t n_rigid = (size_t)P * P + P + 1, n_sum = (size_t)nxt * 64, n_part = (size_t)ch.sm_count * nxt * 64;
   cudaError_t e = grow(ch.gram.ext_dev, ch.gram.ext_bytes, sizeof(double) * (n_rigid + n_sum + n_part) + sizeof(int32_t) * 2 * (size_t)Pc);
