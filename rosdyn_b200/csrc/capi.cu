@@ -237,6 +237,9 @@ void rdb_chain_destroy(rdb_chain* chain)
   if (chain->gram.fused_partials) cudaFree(chain->gram.fused_partials);
   if (chain->gram.fold_dev) cudaFree(chain->gram.fold_dev);
   if (chain->gram.ext_dev) cudaFree(chain->gram.ext_dev);
+  if (chain->host_arena.base) cudaFree(chain->host_arena.base);
+  for (int k = 0; k < 2; k++)
+    if (chain->host_arena.st[k]) cudaStreamDestroy(chain->host_arena.st[k]);
   GramHostPipe& hp = chain->gram_host;
   for (int k = 0; k < GramHostPipe::NSLOT; k++)
   {
@@ -578,23 +581,36 @@ struct HostPipe
   cudaStream_t st[2] = {nullptr, nullptr};
   std::vector<Plane*> all;
   int64_t chunk = 0;
-  ~HostPipe()
-  {
-    for (Plane* p : all)
-      for (int k = 0; k < 2; k++)
-        if (p->d[k]) cudaFree(p->d[k]);
-    for (int k = 0; k < 2; k++)
-      if (st[k]) cudaStreamDestroy(st[k]);
-  }
-  rdb_status init(int64_t n, int64_t chunk_max, std::vector<Plane*> planes)
+  // device buffers and streams come from the handle's arena (grown on demand, freed with the handle); one host call at a time per handle
+  rdb_status init(HostArena& ar, int64_t n, int64_t chunk_max, std::vector<Plane*> planes)
   {
     all = planes;
     chunk = std::min<int64_t>(std::max<int64_t>(n, 1), chunk_max);
     const int slots = n > chunk ? 2 : 1;
-    for (int k = 0; k < slots; k++) RDB_CUDA(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++)
+    {
+      if (!ar.st[k]) RDB_CUDA(cudaStreamCreateWithFlags(&ar.st[k], cudaStreamNonBlocking));
+      st[k] = ar.st[k];
+    }
+    size_t need = 0;
+    for (Plane* p : all)
+      if ((p->h_in || p->h_out) && p->planes > 0) need += sizeof(double) * (size_t)p->planes * chunk * slots;
+    if (ar.bytes < need)
+    {
+      if (ar.base) cudaFree(ar.base);
+      ar.base = nullptr;
+      ar.bytes = 0;
+      RDB_CUDA(cudaMalloc(&ar.base, need));
+      ar.bytes = need;
+    }
+    double* cur = ar.base;
     for (Plane* p : all)
       if ((p->h_in || p->h_out) && p->planes > 0)
-        for (int k = 0; k < slots; k++) RDB_CUDA(cudaMalloc(&p->d[k], sizeof(double) * p->planes * chunk));
+        for (int k = 0; k < slots; k++)
+        {
+          p->d[k] = cur;
+          cur += (size_t)p->planes * chunk;
+        }
     return RDB_OK;
   }
   rdb_status h2d(Plane& p, int slot, int64_t off, int64_t len)
@@ -669,7 +685,7 @@ rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* 
     all.push_back(&po[k]);
   }
   HostPipe pipe;
-  RDB_TRY(pipe.init(in->n, 1 << 20, all));
+  RDB_TRY(pipe.init(const_cast<rdb_chain*>(chain)->host_arena, in->n, 1 << 20, all));
   int slot = 0;
   for (int64_t off = 0; off < in->n; off += pipe.chunk, slot ^= 1)
   {
@@ -699,7 +715,7 @@ static rdb_status dyn_host(const rdb_chain* chain, const rdb_samples* in, double
   ptau.h_out = torque; ptau.planes = torque ? n_in : 0; ptau.ld = ld_out;
   pM.h_out = inertia; pM.planes = inertia ? (int64_t)n_in * n_in : 0; pM.ld = ld_out;
   HostPipe pipe;
-  RDB_TRY(pipe.init(in->n, phi ? (1 << 18) : (1 << 21), {&hi.q, &hi.dq, &hi.ddq, &hi.dddq, &pphi, &ptau, &pM}));
+  RDB_TRY(pipe.init(const_cast<rdb_chain*>(chain)->host_arena, in->n, phi ? (1 << 18) : (1 << 21), {&hi.q, &hi.dq, &hi.ddq, &hi.dddq, &pphi, &ptau, &pM}));
   int slot = 0;
   for (int64_t off = 0; off < in->n; off += pipe.chunk, slot ^= 1)
   {

@@ -54,6 +54,15 @@ struct ComponentParams
   double p[3 * RDB_MAX_COMPONENTS];
 };
 
+// staging arena of the *_host entry points (kinematics / torque / regressor / inertia): device buffers and streams kept in the handle, so that
+// a host call does not pay cudaMalloc / cudaFree of its (up to GB-sized) double buffers every time
+struct HostArena
+{
+  double* base = nullptr;
+  size_t bytes = 0;
+  cudaStream_t st[2] = {nullptr, nullptr};
+};
+
 struct ChainHost
 {
   ComponentsDev comps{};
@@ -64,6 +73,7 @@ struct ChainHost
   double nominal[10 * RDB_MAX_JOINTS];
   GramWorkspace gram;
   GramHostPipe gram_host;
+  HostArena host_arena;
   int sm_count = 148;
   uint64_t model_version = 0;  // bumped by every upload of the model (creation, rdb_chain_set_input_joints)
 };
