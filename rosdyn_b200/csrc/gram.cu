@@ -4,9 +4,11 @@
 // The contraction index k runs over (sample, input-row) pairs; the augmented row [Phi_row | tau_row] gives
 // G, b and tau^T tau from one symmetric rank-k update of a (P+1)x(P+1) matrix.
 //
-// v0 pipeline (general, any chain):  materialise Phi for a chunk of samples into an L2-sized workspace
-// (dyn_kernel) -> syrk_dmma_kernel streams it back (L2 hits) into per-CTA partials -> fixed-order reduction
-// (bit-reproducible for a given launch geometry).
+// General pipeline (any chain; the fused kernels of gram_fused.cu take over whenever the folded chain has at most 7 moving joints):
+// materialise Phi for a chunk of samples into an L2-sized workspace (dyn_kernel) -> syrk_dmma_kernel streams it back (L2 hits) into
+// per-CTA partials -> fixed-order reduction (bit-reproducible for a given launch geometry).  Correct for every chain and component
+// set, but slow: it multiplies all structural zeros and feeds 9 DMMAs from 6 dependent L2 loads (0.076 G samples/s for the extended C6
+// model, against 0.73 on the fused path).
 #include <cuda_runtime.h>
 
 #include <algorithm>
