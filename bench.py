@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target length of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pageable", action="store_true", help="e2e leg with pageable (malloc) host buffers instead of pinned ones")
     return ap.parse_args()
 
 
@@ -111,6 +112,40 @@ def ncu_traffic_per_sample(kernel: str):
         return float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]["dram_bytes_per_sample"])
     except Exception:
         return None
+
+
+def sass_counts(key: str):
+    """FP64 instructions of the named kernel counted in its SASS (profiles/gram_fused_sass.json, written by tools/sass_counts.py at build time
+    from the cubin that ships): {"gen_dp_instr_per_sample": .., "gen_flop_per_sample": .., "dmma_per_4_samples": ..}; None when absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "gram_fused_sass.json")))[key]
+    except Exception:
+        return None
+
+
+def h2d_probe(dev, world, nbytes=1 << 30, reps=3):
+    """Bare pinned-host -> device cudaMemcpyAsync bandwidth of this rank while ALL ranks copy at the same time (GB/s): the ceiling of any
+    end-to-end number on this box (PCIe link per GPU at N = 1; host memory / PCIe fabric shared by the ranks at N > 1)."""
+    import torch
+    import torch.distributed as dist
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    src.fill_(1)
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    t = torch.tensor([gbs], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t[0])
 
 
 def measured_peaks():
@@ -244,11 +279,14 @@ def main():
         run_reference(args)
         return
 
+    import ctypes
+
     import torch
     import torch.distributed as dist
     from rosdyn_b200 import fixtures
+    from rosdyn_b200._lib import CSamples, check, load
     from rosdyn_b200.chain import Chain, fill_uniform, fp64_peak, kernel_launch_count
-    from rosdyn_b200.sharding import allreduce_normal_equations
+    from rosdyn_b200.sharding import Group
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -265,34 +303,45 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     d = fixtures.by_name(args.chain)
-    ch = Chain(d)
+    lib = load()
     n_in, P = d.n_inputs, 10 * d.n_joints
     gram = args.workload == "gram"
-    S = args.samples or (8_000_000 if gram else 4_000_000)        # per GPU per step; inputs (and outputs) >> 126 MB L2
+    # Samples per GPU per step.  gram: 64 M samples = 9.2 GB of device-resident inputs, ~35 ms per step, so the driver's 20 steps give a timed
+    # region of >= 0.7 s under sustained clocks / power (8 M samples per step, round 1, timed 0.1 s of burst clocks).  materialise: a step is
+    # `launches` back-to-back launches of 4 M samples each over DISTINCT inputs; Phi (13.6 GB per launch) is overwritten in place.
+    if gram:
+        S, launches = (args.samples or 64_000_000), 1
+        Sl = S
+    else:
+        Sl = 4_000_000
+        launches = max(1, (args.samples or 32_000_000) // Sl)
+        S = Sl * launches
     # weak scaling: every rank owns its own shard of S samples (disjoint sample indices via the seed offset)
     q, dq, ddq = (fill_uniform(n_in, S, SEED + 1000003 * rank, s, device=dev) for s in range(3))
     if gram:
+        # N > 1: the C-ABI's NCCL group (rdb_group_create_rank): fused kernel -> packed partials -> ncclAllReduce -> caller's arrays, all on
+        # one stream below the C-ABI; torch.distributed only carries the 128-byte NCCL id and the barriers
+        grp = Group.from_torch_distributed(d, local)
+        ch_h = ctypes.c_void_p(lib.rdb_group_chain(grp._h, 0))
         G = torch.zeros((P, P), dtype=torch.float64, device=dev)
         b = torch.zeros((P,), dtype=torch.float64, device=dev)
         tt = torch.zeros((1,), dtype=torch.float64, device=dev)
-        flat = torch.zeros((P * P + P + 1,), dtype=torch.float64, device=dev)
+        out = [(G, b, tt)]
+        shards = [(q, dq, ddq)]
     else:
-        phi = torch.empty((P * n_in, S), dtype=torch.float64, device=dev)
-        tau = torch.empty((n_in, S), dtype=torch.float64, device=dev)
-
-    import ctypes
-    from rosdyn_b200._lib import CSamples, check, load
-    lib = load()
-    smp = CSamples(S, S, q.data_ptr(), dq.data_ptr(), ddq.data_ptr(), None)
+        ch = Chain(d)
+        ch_h = ch._h
+        phi = torch.empty((P * n_in, Sl), dtype=torch.float64, device=dev)
+        tau = torch.empty((n_in, Sl), dtype=torch.float64, device=dev)
+        smps = [CSamples(Sl, S, q[:, k * Sl:].data_ptr(), dq[:, k * Sl:].data_ptr(), ddq[:, k * Sl:].data_ptr(), None) for k in range(launches)]
 
     def step():
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         if gram:
-            check(lib.rdb_regressor_gram_batch(ch._h, ctypes.byref(smp), None, G.data_ptr(), b.data_ptr(), tt.data_ptr(), 0, st))
-            if world > 1:   # the one exchange step of the path: sum the small normal-equation partials over NVLink
-                allreduce_normal_equations(G, b, tt, flat=flat)
+            grp.gram(shards, out=out)     # rdb_regressor_gram_sharded on torch's current stream (one rank: no collective)
         else:
-            check(lib.rdb_regressor_batch(ch._h, ctypes.byref(smp), phi.data_ptr(), tau.data_ptr(), S, st))
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            for smp in smps:
+                check(lib.rdb_regressor_batch(ch_h, ctypes.byref(smp), phi.data_ptr(), tau.data_ptr(), Sl, st))
 
     def barrier():
         if world > 1:
@@ -312,7 +361,7 @@ def main():
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
-    launches = kernel_launch_count() - l0
+    launches_timed = kernel_launch_count() - l0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -322,33 +371,36 @@ def main():
     # ------------------------------------------------------------------ e2e through the host-buffer C-ABI entry
     e2e = None
     if not args.no_e2e:
-        Se = args.e2e_samples or (4_000_000 if gram else 500_000)
-        hq, hdq, hddq = (torch.empty((n_in, Se), dtype=torch.float64).pin_memory() for _ in range(3))
+        probe = h2d_probe(dev, world)
+        Se = args.e2e_samples or (16_000_000 if gram else 500_000)
+
+        def host_buf(rows, cols):
+            t_ = torch.empty((rows, cols), dtype=torch.float64)
+            return t_ if args.pageable else t_.pin_memory()
+        hq, hdq, hddq = (host_buf(n_in, Se) for _ in range(3))
         for k, h in enumerate((hq, hdq, hddq)):
             lib.rdb_fill_uniform_host(h.data_ptr(), n_in, Se, Se, SEED + 1000003 * rank, k)
         hs = CSamples(Se, Se, hq.data_ptr(), hdq.data_ptr(), hddq.data_ptr(), None)
         if gram:
-            hG = torch.empty((P, P), dtype=torch.float64).pin_memory()
-            hb = torch.empty((P,), dtype=torch.float64).pin_memory()
-            ht = torch.empty((1,), dtype=torch.float64).pin_memory()
-            hflat = torch.empty((P * P + P + 1,), dtype=torch.float64)
+            hG, hb, ht = host_buf(P, P), host_buf(1, P), host_buf(1, 1)
+            dflat = torch.empty((P * P + P + 1,), dtype=torch.float64, device=dev)
+            hflat = torch.empty((P * P + P + 1,), dtype=torch.float64).pin_memory()
 
             def e2e_step():
-                check(lib.rdb_regressor_gram_batch_host(ch._h, ctypes.byref(hs), None, hG.data_ptr(), hb.data_ptr(), ht.data_ptr(), 0))
-                if world > 1:
+                check(lib.rdb_regressor_gram_batch_host(ch_h, ctypes.byref(hs), None, hG.data_ptr(), hb.data_ptr(), ht.data_ptr(), 0))
+                if world > 1:   # the partials of the ranks are summed over NVLink and read back
                     hflat[:P * P] = hG.reshape(-1)
-                    hflat[P * P:P * P + P] = hb
-                    hflat[P * P + P:] = ht
-                    f = hflat.to(dev)
-                    dist.all_reduce(f)
-                    f.cpu()
+                    hflat[P * P:P * P + P] = hb.reshape(-1)
+                    hflat[P * P + P:] = ht.reshape(-1)
+                    dflat.copy_(hflat, non_blocking=True)
+                    dist.all_reduce(dflat)
+                    hflat.copy_(dflat)
             h2d, d2h = 3 * n_in * Se * 8, (P * P + P + 1) * 8
         else:
-            hphi = torch.empty((P * n_in, Se), dtype=torch.float64).pin_memory()
-            htau = torch.empty((n_in, Se), dtype=torch.float64).pin_memory()
+            hphi, htau = host_buf(P * n_in, Se), host_buf(n_in, Se)
 
             def e2e_step():
-                check(lib.rdb_regressor_batch_host(ch._h, ctypes.byref(hs), hphi.data_ptr(), htau.data_ptr(), Se))
+                check(lib.rdb_regressor_batch_host(ch_h, ctypes.byref(hs), hphi.data_ptr(), htau.data_ptr(), Se))
             h2d, d2h = 3 * n_in * Se * 8, (P * n_in + n_in) * Se * 8
         for _ in range(2):
             e2e_step()
@@ -361,12 +413,17 @@ def main():
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * Se * ke / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "samples_per_step_per_gpu": Se, "steps": ke,
-               "api": "rdb_regressor_gram_batch_host" if gram else "rdb_regressor_batch_host"}
+        sec = float(te[0])
+        link_gbs = (h2d + d2h) * ke / sec / 1e9       # bytes this rank moved over its PCIe link per second
+        e2e = {"value": world * Se * ke / sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "samples_per_step_per_gpu": Se, "steps": ke, "host_buffers": "pageable" if args.pageable else "pinned",
+               "api": "rdb_regressor_gram_batch_host" if gram else "rdb_regressor_batch_host",
+               "link_GBps_per_gpu": link_gbs, "h2d_probe_GBps_per_gpu": probe, "frac_of_h2d": link_gbs / probe if probe else None,
+               "probe": "bare pinned cudaMemcpyAsync H2D of 1 GiB x 3 on every rank at the same time (min over ranks): the box's ceiling"}
 
     # ------------------------------------------------------------------ roofline of the dominant kernel
     peaks, src = measured_peaks()
+    per_launch_s = ms * 1e-3 / args.steps / launches
     if gram:
         # algorithmic FLOPs per sample, BLAS SYRK+GEMV convention: n_act*P*(P+1) + 2*n_act*P
         flop = n_in * P * (P + 1) + 2 * n_in * P
@@ -374,51 +431,68 @@ def main():
         if rank == 0:
             peaks64 = {"dmma_m8n8k4": fp64_peak("dmma", 3), "dfma": fp64_peak("dfma", 3), "dmma_and_dfma_interleaved": fp64_peak("mixed", 3)}
             peak = max(peaks64["dmma_m8n8k4"], peaks64["dfma"])
-        ach = S * flop / (ms * 1e-3 / args.steps) / 1e12
-        tps = ncu_traffic_per_sample(f"gram_fused_kernel<{d.n_joints}>:{args.chain}")
-        # what the kernel actually executes: joints that never move (fixed / not an input) are folded out of the chain (fold.cpp:
-        # fold_chain), and of the (P'+1)x(P'+1) augmented Gram matrix only the upper-triangular 8x8 tiles right of each row's first
-        # non-zero column are multiplied (one DMMA m8n8k4 = 512 flop per tile per 4 samples)
+        ach = Sl * flop / per_launch_s / 1e12
         K = sum(1 for j in d.joints if j.input_index >= 0)
-        # the row of joint j spans the first ceil((1 + 10 (K - j)) / 8) tiles (the kernel orders the columns tau, last link ... first link)
-        dmma4 = sum(((1 + 10 * (K - j) + 7) // 8) * ((1 + 10 * (K - j) + 7) // 8 + 1) // 2 for j in range(K))
-        ex = dmma4 * 512 / 4
-        sps = S / (ms * 1e-3 / args.steps)
+        tps = ncu_traffic_per_sample(f"gram_fused_kernel<{d.n_joints}>:{args.chain}")
+        # What the kernel executes (counted in the SASS of the cubin that ships, tools/sass_counts.py): per sample, DMMA m8n8k4 tiles of the
+        # folded, structurally non-zero part of the augmented Gram matrix (512 flop each, 4 samples per tile) and the FP64 instructions of the
+        # regressor generation (DFMA = 2 flop, DMUL / DADD = 1 flop).  Both share ONE FP64 datapath: a DMMA holds it 16 cycles, any other FP64
+        # warp instruction 2 cycles, so `datapath_busy_frac` = (16 * DMMA + 2 * FP64 instr) per sample / available datapath cycles per sample.
+        rev = all(j.type == 1 for j in d.joints if j.input_index >= 0)
+        sc = sass_counts(f"K{K}_{'rev' if rev else 'gen'}") or {}
+        sps = Sl / per_launch_s
+        dmma4 = sc.get("dmma_per_4_samples")
+        ex = None
+        if dmma4 is not None and peak:
+            dmma_flop = dmma4 * 512 / 4
+            gen_flop = sc.get("gen_flop_per_sample", 0.0)
+            gen_instr = sc.get("gen_dp_instr_per_sample", 0.0)
+            sm_clock = (clk.summary()["sm_mhz"] or 1965.0) * 1e6
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            cycles_avail = n_sm * 4 * sm_clock / sps                       # FP64-datapath cycles (one datapath per SM sub-partition) per sample
+            cycles_used = 16.0 * dmma4 / 4 + 2.0 * gen_instr / 32     # a generator warp instruction serves 32 samples
+            ex = {"moving_joints": K, "dmma_per_4_samples": dmma4, "dmma_flop_per_sample": dmma_flop, "generation_flop_per_sample": gen_flop,
+                  "generation_fp64_instr_per_sample": gen_instr, "executed_tflops": sps * (dmma_flop + gen_flop) / 1e12,
+                  "executed_flop_frac": sps * (dmma_flop + gen_flop) / 1e12 / peak,
+                  "dmma_frac_of_peak": sps * dmma_flop / 1e12 / peak,
+                  "datapath_busy_frac": cycles_used / cycles_avail,
+                  "note": "achieved/frac use the ALGORITHMIC flops of the reference's dense n_act x 10nJ regressor (SYRK+GEMV convention, SURVEY.md 8d); "
+                          "structural zeros and rigidly attached links are not multiplied, so frac can exceed 1.  executed_* count what the kernel "
+                          "really issues (DMMA tiles + regressor generation); datapath_busy_frac is their occupancy of the FP64 datapath at the "
+                          "SM clock sampled during the run."}
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None,
-                "traffic": (tps * S) if tps else None,
+                "traffic": (tps * Sl) if tps else None,
                 "peak_source": "own FP64 micro-benchmark on this GPU (max of DMMA m8n8k4 and DFMA); MEASURED_PEAKS.json has no FP64 figure",
-                "fp64_peaks_tflops": peaks64, "flop_per_sample": flop,
-                "executed": {"moving_joints": K, "dmma_per_4_samples": dmma4, "dmma_flop_per_sample": ex, "dmma_tflops": sps * ex / 1e12,
-                             "dmma_frac_of_peak": (sps * ex / 1e12 / peak) if peak else None,
-                             "note": "achieved/frac use the ALGORITHMIC flops of the reference's dense n_act x 10nJ regressor (SYRK+GEMV convention, "
-                                     "SURVEY.md 8d); structural zeros and rigidly attached links are not multiplied, so frac can exceed 1. "
-                                     "The regressor generation (~5 kflop/sample of DFMA) shares the same FP64 datapath and is not counted here."},
+                "fp64_peaks_tflops": peaks64, "flop_per_sample": flop, "executed": ex,
                 "kernel": f"gram_fused_kernel<{K},slots> on the folded chain (regressor generation + DMMA normal equations)"}
     else:
         bytes_per_sample = 8 * (3 * n_in + P * n_in + n_in)          # 3552 B for C6
-        ach = S * bytes_per_sample / (ms * 1e-3 / args.steps) / 1e9
+        ach = Sl * bytes_per_sample / per_launch_s / 1e9
         peak = float(peaks["hbm_gbs"])
         tps = ncu_traffic_per_sample(f"dyn_kernel<{d.n_joints},3>:{args.chain}")
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (tps * S) if tps else None,
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": (tps * Sl) if tps else None,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({src})", "bytes_per_sample": bytes_per_sample, "kernel": f"dyn_kernel<{d.n_joints},3> (regressor+torque)"}
 
     if old_affinity is not None:
         os.sched_setaffinity(0, old_affinity)
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.chain, args.cpu_seconds)
-        out = {
+        out_line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": (f"{d.name}: getRegressor ({n_in}x{P}) + getJointTorque per sample, "
                                     + ("fused into Phi^T Phi / Phi^T tau normal equations" if gram else f"materialised as {P * n_in + n_in} SoA planes in HBM")),
-                       "chain": d.name, "samples_per_step_per_gpu": S, "mode": args.workload,
-                       "l2": "inputs (and outputs) per step are far larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"{world} x independent sample shards" + (" + NCCL all-reduce of the partials" if gram and world > 1 else "")},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
+                       "chain": d.name, "samples_per_step_per_gpu": S, "launches_per_step": launches, "mode": args.workload,
+                       "timed_region_s": ms * 1e-3,
+                       "l2": "inputs (and outputs) per launch are far larger than the 126 MB L2; no flush needed",
+                       "parallelism": f"{world} x independent sample shards" + (" + one ncclAllReduce of the partials inside the C-ABI group (rdb_regressor_gram_sharded)" if gram and world > 1 else "")},
+            "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roof, "cpu_baseline": cpu, "clocks": clk.summary(),
         }
         sys.stdout.flush()
-        os.write(real_stdout, (json.dumps(out) + "\n").encode())
+        os.write(real_stdout, (json.dumps(out_line) + "\n").encode())
+    if gram:
+        del grp
     if world > 1:
         dist.destroy_process_group()
 

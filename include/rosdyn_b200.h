@@ -19,7 +19,11 @@
  *     inertia n x n) use plane index  col*rows + row;
  *   - every batched evaluation is STATELESS: each sample is a fresh evaluation through the reference's
  *     direct path (the reference's dirty-flag caches, PI.h:886/985/1088, are not reproduced);
- *   - `stream` is a cudaStream_t passed as void*; device entry points are asynchronous on it.
+ *   - `stream` is a cudaStream_t passed as void*; device entry points are asynchronous on it;
+ *   - a handle lives on ONE device (the current device at rdb_chain_create, or the one given to rdb_chain_create_on); every entry point
+ *     makes that device current for the call and restores the caller's device, so handles of several devices can be driven from one thread;
+ *   - entries that take `const rdb_chain*` only read the handle and may run concurrently on one handle (distinct streams); entries that take
+ *     `rdb_chain*` use per-handle workspaces and are serialised by a per-handle lock.
  *
  * There is no CPU fallback: every compute entry fails with RDB_ERR_NO_DEVICE when no CUDA device exists.
  */
@@ -32,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RDB_ABI_VERSION 1
+#define RDB_ABI_VERSION 2
 #define RDB_MAX_JOINTS 64 /* chain joints incl. fixed (reference: NUM_MAX_AXES 40, internal/types.h:126) */
 
 typedef int32_t rdb_status;
@@ -136,10 +140,28 @@ typedef struct rdb_samples
   const double* dddq; /* [n_inputs][ld] or NULL (== 0)                                                     */
 } rdb_samples;
 
-/* Kinematics outputs; every pointer is optional (NULL = not produced). nL = n_joints + 1. */
+/* Output layout of the batched entries that have a `layout` selector (reference containers: internal/types.h:137-141).
+ *   RDB_LAYOUT_SOA   : SoA planes x[component][ld] as described at the top of this file (the fast layout: coalesced stores).
+ *   RDB_LAYOUT_EIGEN : one dense record per sample, laid out exactly as the reference's Eigen object lies in memory, so a host
+ *                      (or device) `Eigen::Map` can view sample i at  base + i * record  with no conversion; `ld` is ignored:
+ *       poses       Eigen::Affine3d image: 16 doubles, 4x4 COLUMN-major incl. the [0 0 0 1] row; T_tool[n][16],
+ *                   T_links[n][nL][16] (= the storage of a VectorOfAffine3d, T.h:137)
+ *       6-vectors   [n][nL][6]                      (= VectorOfVector6d, T.h:138)
+ *       jacobian    [n][6 * n_inputs]   column-major 6 x n_inputs   (Matrix6Xd)
+ *       regressor   [n][n_inputs * 10 * n_joints] column-major n_inputs x 10 n_joints (Eigen::MatrixXd as getRegressor returns it)
+ *       inertia     [n][n_inputs * n_inputs], torque [n][n_inputs]
+ *     Stores are strided per thread (one record per sample) and reach about half the SoA rate on the device; for a host consumer the
+ *     records come back with ONE contiguous copy per chunk instead of one strided copy per plane. */
+enum
+{
+  RDB_LAYOUT_SOA = 0,
+  RDB_LAYOUT_EIGEN = 1
+};
+
+/* Kinematics outputs; every pointer is optional (NULL = not produced). nL = n_joints + 1.  Zero-initialise the struct: `layout` = 0 is SoA. */
 typedef struct rdb_kinematics_out
 {
-  int64_t ld;             /* plane stride of every output below, ld >= n                                    */
+  int64_t ld;             /* plane stride of every output below, ld >= n  (RDB_LAYOUT_SOA)                  */
   double* T_tool;         /* [12][ld]        Chain::getTransformation            PI.h:884                   */
   double* T_links;        /* [nL][12][ld]    Chain::getTransformations           PI.h:908                   */
   double* jacobian;       /* [n_inputs*6][ld] Chain::getJacobian, plane col*6+row PI.h:927                  */
@@ -151,7 +173,18 @@ typedef struct rdb_kinematics_out
   double* ddtwist_lin;    /* [nL][6][ld]     Chain::getDDTwistLinearPart         PI.h:1126 (correct buffer) */
   double* ddtwist_nonlin; /* [nL][6][ld]     Chain::getDDTwistNonLinearPart      PI.h:1156                  */
   double* torque;         /* [n_inputs][ld]  Chain::getJointTorque (no ext. wrench) PI.h:1277               */
+  int32_t layout;         /* RDB_LAYOUT_SOA (0) or RDB_LAYOUT_EIGEN: shapes above become the per-sample records */
 } rdb_kinematics_out;
+
+/* Dynamics outputs of rdb_dynamics_batch; every pointer is optional.  P = 10 * n_joints. */
+typedef struct rdb_dynamics_out
+{
+  int64_t ld;        /* plane stride (RDB_LAYOUT_SOA), ld >= n                                                      */
+  double* regressor; /* [P * n_inputs][ld], plane col*n_inputs+row   Chain::getRegressor      PI.h:1295            */
+  double* torque;    /* [n_inputs][ld]                               Chain::getJointTorque    PI.h:1277            */
+  double* inertia;   /* [n_inputs * n_inputs][ld], plane col*n_inputs+row  Chain::getJointInertia PI.h:1357        */
+  int32_t layout;    /* RDB_LAYOUT_SOA (0) or RDB_LAYOUT_EIGEN                                                      */
+} rdb_dynamics_out;
 
 /* ---- batched device entry points (pointers are DEVICE pointers) ----------------------------------- */
 /* FK, Jacobian, twist / acceleration / jerk recursions and RNEA torque in one pass over the chain. */
@@ -167,6 +200,10 @@ rdb_status rdb_regressor_batch(const rdb_chain* chain, const rdb_samples* in, do
 /* Chain::getJointInertia (PI.h:1357-1379): inertia[n_inputs*n_inputs][ld_out], plane col*n_inputs+row. */
 rdb_status rdb_inertia_batch(const rdb_chain* chain, const rdb_samples* in, double* inertia, int64_t ld_out, void* stream);
 
+/* getRegressor / getJointTorque / getJointInertia of the same samples with a selectable output layout (the three entries above are the
+ * SoA special cases).  Regressor and torque come from one pass over the chain, the inertia from a second launch. */
+rdb_status rdb_dynamics_batch(const rdb_chain* chain, const rdb_samples* in, const rdb_dynamics_out* out, void* stream);
+
 /* Fused regressor -> normal equations (no reference code: the consumer rosdyn_identification is external,
  * reference README.md:15).  With P = 10*n_joints and Phi_s the n_inputs x P regressor of sample s:
  *   gram[P*P]  (+)= sum_s Phi_s^T Phi_s   (column-major, full symmetric matrix)
@@ -174,7 +211,7 @@ rdb_status rdb_inertia_batch(const rdb_chain* chain, const rdb_samples* in, doub
  *   tau_sq[1]  (+)= sum_s tau_s^T tau_s
  * tau_s = tau_meas[n_inputs][ld] when given, else getJointTorque(q,Dq,DDq) of the sample.
  * accumulate != 0 adds to the existing contents of gram/rhs/tau_sq (chunked / resumable use). */
-rdb_status rdb_regressor_gram_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+rdb_status rdb_regressor_gram_batch(rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                     double* tau_sq, int32_t accumulate, void* stream);
 
 /* Chain::getWrench / Chain::getJointTorque(q,Dq,DDq,ext_wrenches_in_link_frame) (PI.h:1225-1274).
@@ -231,7 +268,8 @@ typedef struct rdb_component_desc
   double max_velocity;
 } rdb_component_desc;
 int32_t rdb_component_columns(int32_t type); /* 2, 3, 2; -1 for an unknown type (ComponentBase::getParametersNumber) */
-rdb_status rdb_chain_set_components(rdb_chain* chain, int32_t n, const rdb_component_desc* components); /* n = 0 clears */
+/* n = 0 clears.  rdb_chain_set_input_joints DROPS the components (their input_index refers to the old input vector): set them again. */
+rdb_status rdb_chain_set_components(rdb_chain* chain, int32_t n, const rdb_component_desc* components);
 int32_t rdb_chain_component_columns(const rdb_chain* chain); /* total number of component columns Pc */
 /* ComponentBase::getRegressor of every component, side by side: phi_c[Pc * n_inputs][ld_out], plane col*n_inputs+row. */
 rdb_status rdb_components_regressor_batch(const rdb_chain* chain, const rdb_samples* in, double* phi_c, int64_t ld_out, void* stream);
@@ -242,7 +280,7 @@ rdb_status rdb_components_torque_batch(const rdb_chain* chain, const rdb_samples
                                        int64_t ld_out, int32_t accumulate, void* stream);
 /* Normal equations of the extended model [Phi | Phi_c] with Pt = 10*n_joints + Pc columns: gram[Pt*Pt], rhs[Pt], tau_sq[1];
  * same conventions as rdb_regressor_gram_batch.  tau_s = tau_meas when given, else the rigid-body getJointTorque. */
-rdb_status rdb_regressor_gram_ext_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+rdb_status rdb_regressor_gram_ext_batch(rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                         double* tau_sq, int32_t accumulate, void* stream);
 
 /* Chain::getMultiplicity (PI.h:1470-1517), HOST arrays: every joint vector q + 2 pi k that stays inside [q_min, q_max], revolute input
@@ -278,16 +316,52 @@ int32_t rdb_chain_device(const rdb_chain* chain);
 rdb_status rdb_regressor_gram_sharded_host(rdb_chain* const* chains, int32_t n_chains, const rdb_samples* in, const double* tau_meas,
                                            double* gram, double* rhs, double* tau_sq, int32_t accumulate);
 
-/* ---- host-buffer convenience wrappers (pointers are HOST pointers; copies + sync inside) ---------- */
-rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out);
-rdb_status rdb_torque_batch_host(const rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out);
-rdb_status rdb_regressor_batch_host(const rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, int64_t ld_out);
-rdb_status rdb_inertia_batch_host(const rdb_chain* chain, const rdb_samples* in, double* inertia, int64_t ld_out);
-rdb_status rdb_regressor_gram_batch_host(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+/* ---- several GPUs over NVLink: the sharded fused Gram with one NCCL all-reduce ----------------
+ * Samples are independent: every device of the group runs the fused regressor -> normal-equation kernel on its own DEVICE-resident shard
+ * and the only exchange is ONE ncclAllReduce(ncclDouble, ncclSum) of the packed partials [gram | rhs | tau_sq] (P^2 + P + 1 doubles) on
+ * each device's stream -- no host round trip.  NCCL is bound at run time (dlopen "libnccl.so.2"; RDB_ERR_NOT_FOUND when a group of more than
+ * one rank is asked for and it is absent).  Two ways to form a group:
+ *   rdb_group_create      one process drives `ndev` devices (ncclCommInitAll); dev_ids NULL = devices 0 .. ndev-1.  This is what a C++
+ *                         consumer such as rosdyn_identification (reference README.md:15) links against;
+ *   rdb_group_create_rank one process per GPU (MPI / torchrun style, ncclCommInitRank): rank 0 calls rdb_group_unique_id and hands the 128
+ *                         bytes to every rank out of band; the group then has ONE local device.
+ * The group owns one chain handle per local device (rdb_group_chain: same chain, usable with every other entry point on that device).
+ * rdb_regressor_gram_sharded: shards[k], tau_meas[k] (array or its entries may be NULL), gram[k] / rhs[k] / tau_sq[k] (entries may be NULL:
+ * that device does not receive the result) are DEVICE pointers on local device k; streams[k] (array or entries may be NULL = the group's own
+ * stream of that device; wait with rdb_group_synchronize).  Every non-NULL output receives the sum over ALL ranks (added to its contents when
+ * accumulate != 0).  Asynchronous.  NCCL's summation order is fixed for a given number of ranks but differs from the single-GPU order:
+ * compare with a tolerance, not bit for bit. */
+typedef struct rdb_group rdb_group; /* opaque */
+rdb_status rdb_group_create(const rdb_chain_desc* desc, int32_t ndev, const int32_t* dev_ids, rdb_group** out);
+rdb_status rdb_group_unique_id(uint8_t id[128]);
+rdb_status rdb_group_create_rank(const rdb_chain_desc* desc, int32_t device, int32_t nranks, int32_t rank, const uint8_t id[128],
+                                 rdb_group** out);
+void rdb_group_destroy(rdb_group* group);
+int32_t rdb_group_size(const rdb_group* group);  /* local devices */
+int32_t rdb_group_ranks(const rdb_group* group); /* ranks of the communicator */
+rdb_chain* rdb_group_chain(rdb_group* group, int32_t k);
+rdb_status rdb_regressor_gram_sharded(rdb_group* group, const rdb_samples* shards, const double* const* tau_meas, double* const* gram,
+                                      double* const* rhs, double* const* tau_sq, int32_t accumulate, void* const* streams);
+rdb_status rdb_group_synchronize(rdb_group* group);
+
+/* ---- host-buffer convenience wrappers (pointers are HOST pointers; copies + sync inside) ----------
+ * The handle is NOT const here: the staging buffers, streams and events of these pipelines live in the handle (grown on demand, freed with
+ * it).  Calls on one handle from several host threads are serialised by a per-handle lock (they do not race, they do not overlap either);
+ * for concurrency use one handle per thread, as the reference does with Chain::clone() (P.h:554).  Pinned (cudaHostAlloc /
+ * cudaHostRegister) buffers overlap the copies with the kernels; pageable buffers work and are staged by the driver (slower). */
+rdb_status rdb_kinematics_batch_host(rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out);
+rdb_status rdb_torque_batch_host(rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out);
+rdb_status rdb_regressor_batch_host(rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, int64_t ld_out);
+rdb_status rdb_inertia_batch_host(rdb_chain* chain, const rdb_samples* in, double* inertia, int64_t ld_out);
+rdb_status rdb_dynamics_batch_host(rdb_chain* chain, const rdb_samples* in, const rdb_dynamics_out* out);
+rdb_status rdb_regressor_gram_batch_host(rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                          double* tau_sq, int32_t accumulate);
 
 /* ---- synthetic inputs (bench / tests): U(-1,1) from splitmix64, identical on host and device ------ */
-/* x[joint][i] = 2*(splitmix64(seed + 32*i + 8*stream + joint) >> 11) * 2^-53 - 1 ; stream 0..3 = q,Dq,DDq,DDDq */
+/* x[plane][i] = 2 * (splitmix64(seed + 256*i + 64*stream_id + plane) >> 11) * 2^-53 - 1   (stream_id 0..3 = q, Dq, DDq, DDDq; plane < 64;
+ * all sums modulo 2^64), with  splitmix64(x): x += 0x9E3779B97F4A7C15; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9;
+ * x = (x ^ (x >> 27)) * 0x94D049BB133111EB; return x ^ (x >> 31).  A reference-side harness that follows this formula gets bit-identical inputs
+ * (tests/test_abi.py checks the documented formula against rdb_fill_uniform_host). */
 rdb_status rdb_fill_uniform(double* x, int32_t n_planes, int64_t n, int64_t ld, uint64_t seed, int32_t stream_id, void* stream);
 void rdb_fill_uniform_host(double* x, int32_t n_planes, int64_t n, int64_t ld, uint64_t seed, int32_t stream_id);
 

@@ -4,8 +4,8 @@
 // * per-sample getters take/return std containers laid out exactly like the reference's Eigen objects
 //   (column-major matrices, 6-vectors linear-then-angular) and run as N = 1 batches on the GPU;
 // * batched siblings take SoA arrays (host or device) and forward to the C-ABI;
-// * optional Eigen-typed overloads appear when <Eigen/Core> is available (it is not in the build image,
-//   so they are compile-tested only where Eigen exists).
+// * Eigen-typed overloads with the reference's signatures appear when <Eigen/Core> is available.  Eigen3 is not in the build image; they are
+//   compile-tested against the Eigen subset of oracle/shim (tests/test_cpp_headers.py) and use element access only.
 // Errors follow the reference: std::runtime_error from the constructor (primitives_impl.h:498-501),
 // std::invalid_argument("Input data dimensions mismatch") from getRegressor (primitives_impl.h:1299-1309).
 // Like the reference class, one object serves one thread at a time.
@@ -23,6 +23,8 @@
 #if defined(__has_include)
 #if __has_include(<Eigen/Core>)
 #include <Eigen/Core>
+#include <Eigen/Geometry>
+#include <Eigen/StdVector>
 #define ROSDYN_B200_HAVE_EIGEN 1
 #endif
 #endif
@@ -73,6 +75,7 @@ public:
   unsigned int getJointsNumber() const { return m_nj; }
   unsigned int getActiveJointsNumber() const { return m_n; }
   const rdb_chain* handle() const { return m_h; }
+  rdb_chain* handle() { return m_h; }
   std::array<double, 3> getGravity() const
   {
     std::array<double, 3> g{};
@@ -96,12 +99,20 @@ public:
   }
 
   // ---------------------------------------------------------------- per-sample getters (reference names)
-  Affine3dImage getTransformation(const VectorXd& q) { return toAffine(kin1(q, nullptr, nullptr, nullptr, &rdb_kinematics_out::T_tool, 12).data()); }
+  // poses come back in the Eigen-record layout of the ABI (RDB_LAYOUT_EIGEN): 16 doubles = the memory image of Eigen::Affine3d
+  Affine3dImage getTransformation(const VectorXd& q)
+  {
+    const VectorXd t = kin1(q, nullptr, nullptr, nullptr, &rdb_kinematics_out::T_tool, 16, RDB_LAYOUT_EIGEN);
+    Affine3dImage T{};
+    for (int k = 0; k < 16; k++) T[k] = t[k];
+    return T;
+  }
   std::vector<Affine3dImage> getTransformations(const VectorXd& q)
   {
-    const VectorXd t = kin1(q, nullptr, nullptr, nullptr, &rdb_kinematics_out::T_links, 12 * m_nl);
+    const VectorXd t = kin1(q, nullptr, nullptr, nullptr, &rdb_kinematics_out::T_links, 16 * m_nl, RDB_LAYOUT_EIGEN);
     std::vector<Affine3dImage> out(m_nl);
-    for (unsigned l = 0; l < m_nl; l++) out[l] = toAffine(t.data() + 12 * l);
+    for (unsigned l = 0; l < m_nl; l++)
+      for (int k = 0; k < 16; k++) out[l][k] = t[16 * l + k];
     return out;
   }
   // 6 x n_act, column-major
@@ -272,23 +283,85 @@ public:
   }
 
 #ifdef ROSDYN_B200_HAVE_EIGEN
-  // Eigen-typed drop-ins for the dynamics getters (same signatures as the reference)
+  // ---------------------------------------------------------------- Eigen-typed drop-ins: the reference's signatures (primitives.h:452-548).
+  // Results are returned BY VALUE (the reference returns const& to member caches that the next call overwrites).  Written with element access
+  // only, so that they compile with Eigen3 proper and with the Eigen subset of oracle/shim (tests/test_cpp_headers.py compiles them there).
+  typedef Eigen::Matrix<double, 6, 1> EVector6d;
+  typedef Eigen::Matrix<double, 6, Eigen::Dynamic> EMatrix6Xd;
+  typedef std::vector<Eigen::Affine3d, Eigen::aligned_allocator<Eigen::Affine3d>> EVectorOfAffine3d;   // internal/types.h:137
+  typedef std::vector<EVector6d, Eigen::aligned_allocator<EVector6d>> EVectorOfVector6d;                 // internal/types.h:138
+
+  Eigen::Affine3d getTransformation(const Eigen::VectorXd& q) { return eAffine(getTransformation(stdv(q))); }
+  EVectorOfAffine3d getTransformations(const Eigen::VectorXd& q)
+  {
+    const std::vector<Affine3dImage> t = getTransformations(stdv(q));
+    EVectorOfAffine3d out;
+    for (const Affine3dImage& a : t) out.push_back(eAffine(a));
+    return out;
+  }
+  EMatrix6Xd getJacobian(const Eigen::VectorXd& q)
+  {
+    const VectorXd j = getJacobian(stdv(q));
+    EMatrix6Xd J(6, (int)m_n);
+    for (unsigned c = 0; c < m_n; c++)
+      for (int r = 0; r < 6; r++) J(r, c) = j[6 * c + r];
+    return J;
+  }
+  EVectorOfVector6d getTwist(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq) { return eSix(getTwist(stdv(q), stdv(Dq))); }
+  EVector6d getTwistTool(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq) { return getTwist(q, Dq).back(); }
+  EVectorOfVector6d getDTwist(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq, const Eigen::VectorXd& DDq)
+  {
+    return eSix(getDTwist(stdv(q), stdv(Dq), stdv(DDq)));
+  }
+  EVector6d getDTwistTool(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq, const Eigen::VectorXd& DDq) { return getDTwist(q, Dq, DDq).back(); }
+  EVectorOfVector6d getDTwistLinearPart(const Eigen::VectorXd& q, const Eigen::VectorXd& DDq) { return eSix(getDTwistLinearPart(stdv(q), stdv(DDq))); }
+  EVectorOfVector6d getDTwistNonLinearPart(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq) { return eSix(getDTwistNonLinearPart(stdv(q), stdv(Dq))); }
+  EVectorOfVector6d getDDTwist(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq, const Eigen::VectorXd& DDq, const Eigen::VectorXd& DDDq)
+  {
+    return eSix(getDDTwist(stdv(q), stdv(Dq), stdv(DDq), stdv(DDDq)));
+  }
+  EVector6d getDDTwistTool(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq, const Eigen::VectorXd& DDq, const Eigen::VectorXd& DDDq)
+  {
+    return getDDTwist(q, Dq, DDq, DDDq).back();
+  }
+  EVectorOfVector6d getDDTwistLinearPart(const Eigen::VectorXd& q, const Eigen::VectorXd& DDDq) { return eSix(getDDTwistLinearPart(stdv(q), stdv(DDDq))); }
+  EVectorOfVector6d getDDTwistNonLinearPart(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq, const Eigen::VectorXd& DDq)
+  {
+    return eSix(getDDTwistNonLinearPart(stdv(q), stdv(Dq), stdv(DDq)));
+  }
   Eigen::VectorXd getJointTorque(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq, const Eigen::VectorXd& DDq)
   {
-    const VectorXd t = getJointTorque(VectorXd(q.data(), q.data() + q.size()), VectorXd(Dq.data(), Dq.data() + Dq.size()),
-                                      VectorXd(DDq.data(), DDq.data() + DDq.size()));
-    return Eigen::Map<const Eigen::VectorXd>(t.data(), t.size());
+    return eVec(getJointTorque(stdv(q), stdv(Dq), stdv(DDq)));
   }
+  Eigen::VectorXd getJointTorqueNonLinearPart(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq) { return eVec(getJointTorqueNonLinearPart(stdv(q), stdv(Dq))); }
   Eigen::MatrixXd getRegressor(const Eigen::VectorXd& q, const Eigen::VectorXd& Dq, const Eigen::VectorXd& DDq)
   {
-    const VectorXd p = getRegressor(VectorXd(q.data(), q.data() + q.size()), VectorXd(Dq.data(), Dq.data() + Dq.size()),
-                                    VectorXd(DDq.data(), DDq.data() + DDq.size()));
-    return Eigen::Map<const Eigen::MatrixXd>(p.data(), m_n, 10 * m_nj);
+    return eMat(getRegressor(stdv(q), stdv(Dq), stdv(DDq)), (int)m_n, (int)(10 * m_nj));
   }
-  Eigen::MatrixXd getJointInertia(const Eigen::VectorXd& q)
+  Eigen::MatrixXd getJointInertia(const Eigen::VectorXd& q) { return eMat(getJointInertia(stdv(q)), (int)m_n, (int)m_n); }
+  Eigen::VectorXd getNominalParametersEigen() const { return eVec(getNominalParameters()); }
+
+  // Batched siblings for Eigen callers: N samples as the COLUMNS of n_act x N matrices (column-major, i.e. one sample = n_act contiguous
+  // doubles); results come back in the Eigen-record layout (RDB_LAYOUT_EIGEN), so sample i of the regressor is the contiguous column-major
+  // n_act x 10 nJ block at out.data() + i * n_act * 10 nJ -- a plain Eigen::Map<const Eigen::MatrixXd> views it.
+  // (AoS inputs are transposed into SoA planes on the host first; identification data kept as SoA from the start skips that copy through the
+  // rdb_samples overloads above.)
+  void getRegressorBatch(const Eigen::MatrixXd& q, const Eigen::MatrixXd& Dq, const Eigen::MatrixXd& DDq, std::vector<double>& regressor_records,
+                         std::vector<double>* torque_records = nullptr)
   {
-    const VectorXd M = getJointInertia(VectorXd(q.data(), q.data() + q.size()));
-    return Eigen::Map<const Eigen::MatrixXd>(M.data(), m_n, m_n);
+    if (q.rows() != (int)m_n || Dq.rows() != q.rows() || DDq.rows() != q.rows() || Dq.cols() != q.cols() || DDq.cols() != q.cols())
+      throw std::invalid_argument("Input data dimensions mismatch");
+    const int64_t n = (int64_t)q.cols();
+    const VectorXd sq = soa(q), sdq = soa(Dq), sddq = soa(DDq);
+    regressor_records.resize((size_t)n * m_n * 10 * m_nj);
+    if (torque_records) torque_records->resize((size_t)n * m_n);
+    rdb_samples in{n, n > 0 ? n : 1, sq.data(), sdq.data(), sddq.data(), nullptr};
+    rdb_dynamics_out out{};
+    out.ld = in.ld;
+    out.layout = RDB_LAYOUT_EIGEN;
+    out.regressor = regressor_records.data();
+    out.torque = torque_records ? torque_records->data() : nullptr;
+    check(rdb_dynamics_batch_host(m_h, &in, &out));
   }
 #endif
 
@@ -307,25 +380,62 @@ private:
     if (q.size() != m_n || (a && a->size() != m_n) || (b && b->size() != m_n) || (c && c->size() != m_n))
       throw std::invalid_argument("Input data dimensions mismatch");
   }
-  VectorXd kin1(const VectorXd& q, const VectorXd* Dq, const VectorXd* DDq, const VectorXd* DDDq, double* rdb_kinematics_out::*field, size_t rows)
+  VectorXd kin1(const VectorXd& q, const VectorXd* Dq, const VectorXd* DDq, const VectorXd* DDDq, double* rdb_kinematics_out::*field, size_t rows,
+                int32_t layout = RDB_LAYOUT_SOA)
   {
     sizes(q, Dq, DDq, DDDq);
     VectorXd out(rows);
     rdb_samples in{1, 1, q.data(), Dq ? Dq->data() : nullptr, DDq ? DDq->data() : nullptr, DDDq ? DDDq->data() : nullptr};
     rdb_kinematics_out o{};
     o.ld = 1;
+    o.layout = layout;
     o.*field = out.data();
     check(rdb_kinematics_batch_host(m_h, &in, &o));
     return out;
   }
-  static Affine3dImage toAffine(const double* t34)  // 3x4 row-major -> 4x4 column-major
+#ifdef ROSDYN_B200_HAVE_EIGEN
+  static VectorXd stdv(const Eigen::VectorXd& v)
   {
-    Affine3dImage T{};
-    for (int r = 0; r < 3; r++)
-      for (int c = 0; c < 4; c++) T[4 * c + r] = t34[4 * r + c];
-    T[15] = 1.0;
+    VectorXd o((size_t)v.size());
+    for (size_t k = 0; k < o.size(); k++) o[k] = v((int)k);
+    return o;
+  }
+  static Eigen::VectorXd eVec(const VectorXd& v)
+  {
+    Eigen::VectorXd o((int)v.size());
+    for (size_t k = 0; k < v.size(); k++) o((int)k) = v[k];
+    return o;
+  }
+  static Eigen::MatrixXd eMat(const VectorXd& v, int rows, int cols)  // column-major image -> matrix
+  {
+    Eigen::MatrixXd o(rows, cols);
+    for (int c = 0; c < cols; c++)
+      for (int r = 0; r < rows; r++) o(r, c) = v[(size_t)c * rows + r];
+    return o;
+  }
+  static Eigen::Affine3d eAffine(const Affine3dImage& a)
+  {
+    Eigen::Affine3d T;
+    for (int c = 0; c < 4; c++)
+      for (int r = 0; r < 4; r++) T.matrix()(r, c) = a[4 * c + r];
     return T;
   }
+  static EVectorOfVector6d eSix(const std::vector<Vector6d>& v)
+  {
+    EVectorOfVector6d o(v.size());
+    for (size_t l = 0; l < v.size(); l++)
+      for (int k = 0; k < 6; k++) o[l](k) = v[l][k];
+    return o;
+  }
+  static VectorXd soa(const Eigen::MatrixXd& x)  // n_act x N (samples as columns) -> SoA planes x[joint][N]
+  {
+    const int64_t rows = x.rows(), cols = x.cols();
+    VectorXd o((size_t)(rows * cols));
+    for (int64_t r = 0; r < rows; r++)
+      for (int64_t c = 0; c < cols; c++) o[(size_t)(r * cols + c)] = x((int)r, (int)c);
+    return o;
+  }
+#endif
   static std::vector<Vector6d> six(const VectorXd& v)
   {
     std::vector<Vector6d> out(v.size() / 6);

@@ -40,7 +40,8 @@ def build_ref(force: bool = False) -> bool:
     if not os.path.isdir(REFERENCE_ROOT):
         return os.path.exists(REF_LIB)
     deps = [os.path.join(_HERE, "ref_driver.cpp"), os.path.join(_HERE, "shim", "mini_eigen.h"), os.path.join(_HERE, "box_qp.h"),
-            os.path.join(_HERE, "shim", "ros", "ros.h"), os.path.join(_HERE, "shim", "eigen_matrix_utils", "eiquadprog.hpp")]
+            os.path.join(_HERE, "shim", "ros", "ros.h"), os.path.join(_HERE, "shim", "eigen_matrix_utils", "eiquadprog.hpp"),
+            os.path.join(_HERE, "..", "include", "rosdyn_b200", "rosdyn_core_bridge.h")]
     if force or not os.path.exists(REF_LIB) or any(os.path.getmtime(REF_LIB) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
     return True

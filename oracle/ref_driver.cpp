@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../include/rosdyn_b200.h" /* descriptor structs only */
+#include "../include/rosdyn_b200/rosdyn_core_bridge.h" /* the reference-side binding under test: rosdyn::Chain -> rdb_chain_desc (no GPU) */
 
 namespace
 {
@@ -501,6 +502,21 @@ void oracle_components_regressor_batch(int n_comp, const rdb_component_desc* com
     }
     col += nc;
   }
+}
+
+// The reference-side binding (include/rosdyn_b200/rosdyn_core_bridge.h) run on the reference's own Chain: joints[nJ], links[nJ + 1],
+// gravity[3] as rosdyn::toB200Desc reports them; returns the number of inputs.  tests/test_cpp_headers.py feeds the result back into the
+// restatement and compares it with the reference's outputs on the original chain.
+int oracle_bridge_descriptor(void* cv, rdb_joint_desc* joints, rdb_link_desc* links, double gravity[3])
+{
+  RefChain& rc = *static_cast<RefChain*>(cv);
+  std::vector<rdb_joint_desc> J;
+  std::vector<rdb_link_desc> L;
+  const rdb_chain_desc d = rosdyn::toB200Desc(*rc.chain, J, L);
+  for (size_t k = 0; k < J.size(); k++) joints[k] = J[k];
+  for (size_t k = 0; k < L.size(); k++) links[k] = L[k];
+  for (int k = 0; k < 3; k++) gravity[k] = d.gravity[k];
+  return d.n_inputs;
 }
 
 }  // extern "C"

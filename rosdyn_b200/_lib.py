@@ -8,7 +8,7 @@ import os
 from .descriptor import CChainDesc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("RDB_LIB_PATH") or os.path.join(HERE, "librosdyn_b200.so")  # override: kernel A/B experiments only
+LIB_PATH = os.path.join(HERE, "librosdyn_b200.so")  # the in-tree build, nothing else (no environment override)
 
 _dp = ctypes.c_void_p  # device or host pointer to double
 i32, i64, u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
@@ -22,8 +22,15 @@ KIN_FIELDS = ("T_tool", "T_links", "jacobian", "twist", "dtwist", "dtwist_lin", 
               "ddtwist_nonlin", "torque")
 
 
+RDB_LAYOUT_SOA, RDB_LAYOUT_EIGEN = 0, 1
+
+
 class CKinematicsOut(ctypes.Structure):
-    _fields_ = [("ld", i64)] + [(k, _dp) for k in KIN_FIELDS]
+    _fields_ = [("ld", i64)] + [(k, _dp) for k in KIN_FIELDS] + [("layout", i32)]
+
+
+class CDynamicsOut(ctypes.Structure):
+    _fields_ = [("ld", i64), ("regressor", _dp), ("torque", _dp), ("inertia", _dp), ("layout", i32)]
 
 
 class CUrdfChain(ctypes.Structure):
@@ -58,6 +65,8 @@ SYMBOLS = {
     "rdb_torque_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, ctypes.c_void_p]),
     "rdb_regressor_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, i64, ctypes.c_void_p]),
     "rdb_inertia_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, ctypes.c_void_p]),
+    "rdb_dynamics_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(CDynamicsOut), ctypes.c_void_p]),
+    "rdb_dynamics_batch_host": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(CDynamicsOut)]),
     "rdb_regressor_gram_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, _dp, _dp, _dp, i32, ctypes.c_void_p]),
     "rdb_wrench_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), _dp, i64, _dp, _dp, i64, ctypes.c_void_p]),
     "rdb_jacobian_link_batch": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), i32, _dp, i64, ctypes.c_void_p]),
@@ -84,6 +93,16 @@ SYMBOLS = {
     "rdb_chain_create_on": (i32, [ctypes.POINTER(CChainDesc), i32, ctypes.POINTER(ctypes.c_void_p)]),
     "rdb_chain_device": (i32, [ctypes.c_void_p]),
     "rdb_regressor_gram_sharded_host": (i32, [ctypes.POINTER(ctypes.c_void_p), i32, ctypes.POINTER(CSamples), _dp, _dp, _dp, _dp, i32]),
+    "rdb_group_create": (i32, [ctypes.POINTER(CChainDesc), i32, ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_void_p)]),
+    "rdb_group_unique_id": (i32, [ctypes.POINTER(ctypes.c_uint8)]),
+    "rdb_group_create_rank": (i32, [ctypes.POINTER(CChainDesc), i32, i32, i32, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_void_p)]),
+    "rdb_group_destroy": (None, [ctypes.c_void_p]),
+    "rdb_group_size": (i32, [ctypes.c_void_p]),
+    "rdb_group_ranks": (i32, [ctypes.c_void_p]),
+    "rdb_group_chain": (ctypes.c_void_p, [ctypes.c_void_p, i32]),
+    "rdb_regressor_gram_sharded": (i32, [ctypes.c_void_p, ctypes.POINTER(CSamples), ctypes.POINTER(_dp), ctypes.POINTER(_dp), ctypes.POINTER(_dp),
+                                         ctypes.POINTER(_dp), i32, ctypes.POINTER(ctypes.c_void_p)]),
+    "rdb_group_synchronize": (i32, [ctypes.c_void_p]),
     "rdb_fill_uniform": (i32, [_dp, i32, i64, i64, u64, i32, ctypes.c_void_p]),
     "rdb_fill_uniform_host": (None, [_dp, i32, i64, i64, u64, i32]),
     "rdb_fp64_peak": (i32, [i32, i32, ctypes.POINTER(ctypes.c_double)]),
@@ -98,6 +117,14 @@ class RosdynB200Error(RuntimeError):
     def __init__(self, status: int, text: str):
         super().__init__(f"rosdyn_b200 status {status}: {text}")
         self.status = status
+
+
+def set_library_path(path: str) -> None:
+    """Development tools only (tools/bench_gram.py: A/B runs of experimental builds under build/var_*): must be called before the first load()."""
+    global LIB_PATH
+    if _lib is not None:
+        raise RuntimeError("the library is already loaded")
+    LIB_PATH = path
 
 
 def load() -> ctypes.CDLL:

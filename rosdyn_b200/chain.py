@@ -104,7 +104,7 @@ class Chain:
         sel = (ctypes.c_int32 * max(len(names), 1))(*[idx.get(n, -1) for n in names])
         check(self._lib.rdb_chain_set_input_joints(self._h, len(names), sel))
         ok = self.desc.set_input_joints(names)
-        self.n_in = len(names)
+        self.n_in = len(names)   # note: the C-ABI drops the additive components here (set them again with setComponents)
         return ok
 
     def getNominalParameters(self) -> np.ndarray:
@@ -153,6 +153,20 @@ class Chain:
             outs = [None if a is None else (a.contiguous() if _is_torch(a) else np.ascontiguousarray(a)) for a in outs]
         return dev, single, n, outs
 
+    def _with_tau(self, dev, n, arrs, tau_meas):
+        """Measured torques for the normal equations: same side, same n_act x N shape as q (ValueError otherwise -- a shorter array would be
+        read past its end), and brought to the one plane stride the ABI takes for q / Dq / DDq / tau_meas."""
+        tdev, _, nt, (tau_arr,) = self._prep([tau_meas])
+        if tdev != dev:
+            raise ValueError("all inputs must live on the same side (torch CUDA or host)")
+        if nt != n:
+            raise ValueError("Input data dimensions mismatch")
+        if _ld(tau_arr) != _ld(arrs[0]):
+            tau_arr = tau_arr.contiguous() if _is_torch(tau_arr) else np.ascontiguousarray(tau_arr)
+            if _ld(tau_arr) != _ld(arrs[0]):
+                arrs = [None if a is None else (a.contiguous() if _is_torch(a) else np.ascontiguousarray(a)) for a in arrs]
+        return arrs, tau_arr
+
     def _samples(self, n, arrs) -> CSamples:
         s = CSamples()
         s.n = n
@@ -171,22 +185,69 @@ class Chain:
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------ kinematics
-    def kinematics(self, q, Dq=None, DDq=None, DDDq=None, want: Sequence[str] = ("T_tool",)):
-        """One pass producing any subset of rdb_kinematics_out; returns {name: planes[rows][N]} (raw plane layout)."""
+    def kinematics(self, q, Dq=None, DDq=None, DDDq=None, want: Sequence[str] = ("T_tool",), layout: str = "soa"):
+        """One pass producing any subset of rdb_kinematics_out.  layout "soa": {name: planes[rows][N]} (raw plane layout);
+        layout "eigen": {name: records[N][...]} shaped as the reference's Eigen containers lie in memory (RDB_LAYOUT_EIGEN):
+        poses [N,4,4] views of the column-major Affine3d images (so r[i] reads as the 4x4 matrix), T_links [N,nL,4,4], 6-vectors [N,nL,6],
+        jacobian [N,6,n_act], torque [N,n_act]."""
         dev, single, n, arrs = self._prep([q, Dq, DDq, DDDq])
-        rows = {"T_tool": 12, "T_links": 12 * self.nL, "jacobian": 6 * self.n_in, "torque": self.n_in}
+        eig = {"soa": False, "eigen": True}[layout]
+        pose = 16 if eig else 12
+        rows = {"T_tool": pose, "T_links": pose * self.nL, "jacobian": 6 * self.n_in, "torque": self.n_in}
         out = CKinematicsOut()
         out.ld = max(n, 1)
+        out.layout = _lib.RDB_LAYOUT_EIGEN if eig else _lib.RDB_LAYOUT_SOA
         res = {}
         for k in KIN_FIELDS:
             if k in want:
-                res[k] = self._alloc(dev, rows.get(k, 6 * self.nL), n, arrs[0])
+                r = rows.get(k, 6 * self.nL)
+                res[k] = self._alloc(dev, n, r, arrs[0]) if eig else self._alloc(dev, r, n, arrs[0])
                 setattr(out, k, _ptr(res[k]))
         s = self._samples(n, arrs)
         if dev:
             check(self._lib.rdb_kinematics_batch(self._h, ctypes.byref(s), ctypes.byref(out), self._stream()))
         else:
             check(self._lib.rdb_kinematics_batch_host(self._h, ctypes.byref(s), ctypes.byref(out)))
+        if eig:  # shape the dense records like the Eigen objects (column-major matrices read through a transposed view)
+            for k, r in res.items():
+                if k == "T_tool":
+                    res[k] = _swap_last2(r.reshape(n, 4, 4))
+                elif k == "T_links":
+                    res[k] = _swap_last2(r.reshape(n, self.nL, 4, 4))
+                elif k == "jacobian":
+                    res[k] = _swap_last2(r.reshape(n, self.n_in, 6))
+                elif k != "torque":
+                    res[k] = r.reshape(n, self.nL, 6)
+        return res
+
+    def dynamics(self, q, Dq=None, DDq=None, want: Sequence[str] = ("regressor", "torque"), layout: str = "soa"):
+        """rdb_dynamics_batch: any subset of regressor / torque / inertia with a selectable layout.  "soa": raw planes
+        {regressor [10 nJ * n_act][N], torque [n_act][N], inertia [n_act^2][N]}; "eigen": per-sample records viewed as the Eigen matrices
+        {regressor [N, n_act, 10 nJ], torque [N, n_act], inertia [N, n_act, n_act]} (each record is the column-major matrix)."""
+        if "regressor" in want and (Dq is None or DDq is None):
+            raise ValueError("Input data dimensions mismatch")
+        dev, single, n, arrs = self._prep([q, Dq, DDq, None])
+        eig = {"soa": False, "eigen": True}[layout]
+        P = 10 * self.nJ
+        rows = {"regressor": P * self.n_in, "torque": self.n_in, "inertia": self.n_in * self.n_in}
+        out = _lib.CDynamicsOut()
+        out.ld = max(n, 1)
+        out.layout = _lib.RDB_LAYOUT_EIGEN if eig else _lib.RDB_LAYOUT_SOA
+        res = {}
+        for k in ("regressor", "torque", "inertia"):
+            if k in want:
+                res[k] = self._alloc(dev, n, rows[k], arrs[0]) if eig else self._alloc(dev, rows[k], n, arrs[0])
+                setattr(out, k, _ptr(res[k]))
+        s = self._samples(n, arrs)
+        if dev:
+            check(self._lib.rdb_dynamics_batch(self._h, ctypes.byref(s), ctypes.byref(out), self._stream()))
+        else:
+            check(self._lib.rdb_dynamics_batch_host(self._h, ctypes.byref(s), ctypes.byref(out)))
+        if eig:
+            if "regressor" in res:
+                res["regressor"] = _swap_last2(res["regressor"].reshape(n, P, self.n_in))
+            if "inertia" in res:
+                res["inertia"] = _swap_last2(res["inertia"].reshape(n, self.n_in, self.n_in))
         return res
 
     def _kin1(self, name, shape, q, Dq=None, DDq=None, DDDq=None):
@@ -400,11 +461,7 @@ class Chain:
         dev, single, n, arrs = self._prep([q, Dq, DDq, None])
         tau_arr = None
         if tau_meas is not None:
-            _, _, nt, (tau_arr,) = self._prep([tau_meas])
-            if nt != n or _ld(tau_arr) != _ld(arrs[0]):
-                tau_arr = tau_arr.contiguous() if _is_torch(tau_arr) else np.ascontiguousarray(tau_arr)
-                if _ld(tau_arr) != _ld(arrs[0]):
-                    arrs = [None if a is None else (a.contiguous() if _is_torch(a) else np.ascontiguousarray(a)) for a in arrs]
+            arrs, tau_arr = self._with_tau(dev, n, arrs, tau_meas)
         P = 10 * self.nJ
         acc = out is not None
         if acc:
@@ -482,10 +539,7 @@ class Chain:
             raise ValueError("component entry points take device (torch CUDA) arrays")
         tau_arr = None
         if tau_meas is not None:
-            _, _, nt, (tau_arr,) = self._prep([tau_meas])
-            if nt != n or _ld(tau_arr) != _ld(arrs[0]):
-                tau_arr = tau_arr.contiguous()
-                arrs = [None if a is None else a.contiguous() for a in arrs]
+            arrs, tau_arr = self._with_tau(dev, n, arrs, tau_meas)
         Pt = 10 * self.nJ + self.getComponentColumns()
         acc = out is not None
         if acc:
@@ -516,6 +570,10 @@ def _ld(a) -> int:
 
 def _swap01(a):
     return a.transpose(0, 1) if _is_torch(a) else np.swapaxes(a, 0, 1)
+
+
+def _swap_last2(a):
+    return a.transpose(-1, -2) if _is_torch(a) else np.swapaxes(a, -1, -2)
 
 
 def _affine(r34):

@@ -37,6 +37,13 @@ static rdb_status cuda_fail(cudaError_t e, const char* where)
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
+// entry-point prologue: the handle's device becomes current (restored on return); RDB_LOCK serialises the entries that touch the handle's
+// mutable state (model, workspaces, staging pipelines)
+#define RDB_ENTER(chain)                                                          \
+  DeviceScope dev__((chain)->device);                                             \
+  if (dev__.err != cudaSuccess) return cuda_fail(dev__.err, "cudaSetDevice(device of the handle)")
+#define RDB_LOCK(chain) std::lock_guard<std::recursive_mutex> lock__((chain)->mu)
+
 static void mat3_mul(const double* a, const double* b, double* c)
 {
   for (int i = 0; i < 3; i++)
@@ -119,9 +126,9 @@ static rdb_status build_model(const rdb_chain_desc* d, ChainHost* ch)
   return RDB_OK;
 }
 
+// the handle's device (fixed at creation) must be current: every caller holds a DeviceScope
 static rdb_status upload_model(ChainHost* ch)
 {
-  RDB_CUDA(cudaGetDevice(&ch->device));
   if (!ch->dev) RDB_CUDA(cudaMalloc(&ch->dev, sizeof(ch->host)));
   RDB_CUDA(cudaMemcpy(ch->dev, &ch->host, sizeof(ch->host), cudaMemcpyHostToDevice));
   cudaDeviceGetAttribute(&ch->sm_count, cudaDevAttrMultiProcessorCount, ch->device);
@@ -158,12 +165,14 @@ static unsigned kin_mask(const rdb_kinematics_out* o)
 }
 
 // rows/columns of inputs that no chain joint feeds stay zero in the reference (S has a zero column there)
-static rdb_status prezero(const ChainHost* ch, double* p, int64_t planes, int64_t ld, int64_t n, cudaStream_t st)
+static rdb_status prezero(const ChainHost* ch, double* p, int64_t planes, int64_t ld, int64_t n, cudaStream_t st, bool eigen = false)
 {
-  if (ch->inputs_cover_all || !p || n <= 0) return RDB_OK;
-  RDB_CUDA(cudaMemset2DAsync(p, ld * sizeof(double), 0, n * sizeof(double), planes, st));
+  if (ch->inputs_cover_all || !p || n <= 0 || planes <= 0) return RDB_OK;
+  if (eigen) RDB_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * (size_t)n * planes, st));  // dense per-sample records
+  else RDB_CUDA(cudaMemset2DAsync(p, ld * sizeof(double), 0, n * sizeof(double), planes, st));
   return RDB_OK;
 }
+static bool bad_layout(int32_t l) { return l != RDB_LAYOUT_SOA && l != RDB_LAYOUT_EIGEN; }
 
 }  // namespace rdb
 
@@ -217,6 +226,7 @@ rdb_status rdb_chain_create(const rdb_chain_desc* desc, rdb_chain** out)
   if (s == RDB_OK)
   {
     if (rdb_device_count() <= 0) s = fail(RDB_ERR_NO_DEVICE, "no CUDA device: rosdyn_b200 has no CPU fallback");
+    else if (cudaGetDevice(&ch->device) != cudaSuccess) s = fail(RDB_ERR_CUDA, "cudaGetDevice failed");  // the handle lives on the CURRENT device
     else s = upload_model(ch);
   }
   if (s != RDB_OK)
@@ -232,6 +242,7 @@ rdb_status rdb_chain_create(const rdb_chain_desc* desc, rdb_chain** out)
 void rdb_chain_destroy(rdb_chain* chain)
 {
   if (!chain) return;
+  DeviceScope dev__(chain->device);
   if (chain->dev) cudaFree(chain->dev);
   if (chain->gram.partials) cudaFree(chain->gram.partials);
   if (chain->gram.fused_partials) cudaFree(chain->gram.fused_partials);
@@ -257,6 +268,8 @@ rdb_status rdb_chain_set_input_joints(rdb_chain* chain, int32_t n_inputs, const 
 {
   if (!chain || n_inputs < 0 || n_inputs > RDB_MAX_JOINTS || (n_inputs > 0 && !chain_joint_of_input))
     return fail(RDB_ERR_INVALID_ARG, "bad input-joint selection");
+  RDB_ENTER(chain);
+  RDB_LOCK(chain);
   std::vector<int> in(chain->host.nj, -1);
   bool all = true;
   for (int i = 0; i < n_inputs; i++)
@@ -273,6 +286,9 @@ rdb_status rdb_chain_set_input_joints(rdb_chain* chain, int32_t n_inputs, const 
   for (int j = 0; j < chain->host.nj; j++) chain->host.joint[j].in = in[j];
   chain->host.n_in = n_inputs;
   chain->inputs_cover_all = all;
+  // the components were registered against the OLD input vector (their input_index may be out of range now, or name another joint):
+  // they are dropped and must be set again after the inputs change (the reference builds its components from the joint-name list, base_component.h:95-108)
+  chain->comps = ComponentsDev{};
   return upload_model(chain);
 }
 
@@ -297,16 +313,18 @@ rdb_status rdb_kinematics_batch(const rdb_chain* chain, const rdb_samples* in, c
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
-  if (!out || out->ld < in->n) return fail(RDB_ERR_INVALID_ARG, "kinematics_out: need ld >= n");
+  RDB_ENTER(chain);
+  if (!out || bad_layout(out->layout)) return fail(RDB_ERR_INVALID_ARG, "kinematics_out: null or unknown layout");
+  const bool eig = out->layout == RDB_LAYOUT_EIGEN;
+  if (!eig && out->ld < in->n) return fail(RDB_ERR_INVALID_ARG, "kinematics_out: need ld >= n");
   const unsigned mask = kin_mask(out);
   if (!mask || in->n == 0) return RDB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int nL = chain->host.nj + 1, n_in = chain->host.n_in;
-  if ((s = prezero(chain, out->jacobian, 6 * n_in, out->ld, in->n, st)) != RDB_OK) return s;
-  if ((s = prezero(chain, out->torque, n_in, out->ld, in->n, st)) != RDB_OK) return s;
-  (void)nL;
+  const int n_in = chain->host.n_in;
+  if ((s = prezero(chain, out->jacobian, 6 * n_in, out->ld, in->n, st, eig)) != RDB_OK) return s;
+  if ((s = prezero(chain, out->torque, n_in, out->ld, in->n, st, eig)) != RDB_OK) return s;
   KinOutDev o{out->ld,         out->T_tool,        out->T_links, out->jacobian,    out->twist,          out->dtwist,
-              out->dtwist_lin, out->dtwist_nonlin, out->ddtwist, out->ddtwist_lin, out->ddtwist_nonlin, out->torque};
+              out->dtwist_lin, out->dtwist_nonlin, out->ddtwist, out->ddtwist_lin, out->ddtwist_nonlin, out->torque, eig ? 1 : 0};
   RDB_CUDA(launch_kin(*chain, mask, to_dev(in), o, st));
   return RDB_OK;
 }
@@ -315,6 +333,7 @@ rdb_status rdb_torque_batch(const rdb_chain* chain, const rdb_samples* in, doubl
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
   if (in->n == 0) return RDB_OK;
   if (!torque || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "torque: null or ld_out < n");
   cudaStream_t st = (cudaStream_t)stream;
@@ -327,6 +346,7 @@ rdb_status rdb_regressor_batch(const rdb_chain* chain, const rdb_samples* in, do
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
   // Chain::getRegressor throws std::invalid_argument("Input data dimensions mismatch") (primitives_impl.h:1299-1309)
   if (in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
   if (in->n == 0) return RDB_OK;
@@ -343,6 +363,7 @@ rdb_status rdb_inertia_batch(const rdb_chain* chain, const rdb_samples* in, doub
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
   if (in->n == 0) return RDB_OK;
   if (!inertia || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "inertia: null or ld_out < n");
   cudaStream_t st = (cudaStream_t)stream;
@@ -352,14 +373,39 @@ rdb_status rdb_inertia_batch(const rdb_chain* chain, const rdb_samples* in, doub
   return RDB_OK;
 }
 
-rdb_status rdb_regressor_gram_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+rdb_status rdb_dynamics_batch(const rdb_chain* chain, const rdb_samples* in, const rdb_dynamics_out* out, void* stream)
+{
+  rdb_status s = check_samples(chain, in, true);
+  if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
+  if (!out || bad_layout(out->layout)) return fail(RDB_ERR_INVALID_ARG, "dynamics_out: null or unknown layout");
+  const bool eig = out->layout == RDB_LAYOUT_EIGEN;
+  if (!eig && out->ld < in->n) return fail(RDB_ERR_INVALID_ARG, "dynamics_out: need ld >= n");
+  // Chain::getRegressor throws std::invalid_argument("Input data dimensions mismatch") (primitives_impl.h:1299-1309)
+  if (out->regressor && in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (in->n == 0 || (!out->regressor && !out->torque && !out->inertia)) return RDB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_in = chain->host.n_in, P = (int64_t)10 * chain->host.nj;
+  if ((s = prezero(chain, out->regressor, P * n_in, out->ld, in->n, st, eig)) != RDB_OK) return s;
+  if ((s = prezero(chain, out->torque, n_in, out->ld, in->n, st, eig)) != RDB_OK) return s;
+  if ((s = prezero(chain, out->inertia, n_in * n_in, out->ld, in->n, st, eig)) != RDB_OK) return s;
+  DynOutDev o{out->regressor, out->torque, out->inertia, eig ? 1 : out->ld, eig ? P * n_in : 1, eig ? n_in : 1, eig ? n_in * n_in : 1};
+  if (out->regressor) RDB_CUDA(launch_dyn(*chain, out->torque ? (DYN_REGRESSOR_ | DYN_TORQUE_) : DYN_REGRESSOR_, to_dev(in), o, st));
+  else if (out->torque) RDB_CUDA(launch_dyn(*chain, DYN_TORQUE_, to_dev(in), o, st));
+  if (out->inertia) RDB_CUDA(launch_dyn(*chain, DYN_INERTIA_, to_dev(in), o, st));
+  return RDB_OK;
+}
+
+rdb_status rdb_regressor_gram_batch(rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                     double* tau_sq, int32_t accumulate, void* stream)
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
+  RDB_LOCK(chain);  // the per-CTA partials live in the handle
   if (in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
   if (!gram || !rhs) return fail(RDB_ERR_INVALID_ARG, "gram / rhs must not be null");
-  RDB_CUDA(launch_gram(*const_cast<rdb_chain*>(chain), to_dev(in), tau_meas, gram, rhs, tau_sq, accumulate, (cudaStream_t)stream));
+  RDB_CUDA(launch_gram(*chain, to_dev(in), tau_meas, gram, rhs, tau_sq, accumulate, (cudaStream_t)stream));
   return RDB_OK;
 }
 
@@ -368,6 +414,7 @@ rdb_status rdb_wrench_batch(const rdb_chain* chain, const rdb_samples* in, const
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
   if (in->n == 0 || (!torque && !wrenches)) return RDB_OK;
   if (ld_out < in->n || (ext_wrenches && ld_ext < in->n)) return fail(RDB_ERR_INVALID_ARG, "wrench_batch: ld < n");
   cudaStream_t st = (cudaStream_t)stream;
@@ -381,6 +428,7 @@ rdb_status rdb_jacobian_link_batch(const rdb_chain* chain, const rdb_samples* in
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
   if (link_index < 0 || link_index > chain->host.nj) return fail(RDB_ERR_NOT_FOUND, "link is not member of the chain");
   if (in->n == 0) return RDB_OK;
   if (!jacobian || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "jacobian: null or ld_out < n");
@@ -400,6 +448,7 @@ rdb_status rdb_local_ik_batch(const rdb_chain* chain, int64_t n, int64_t ld, con
   if (n == 0) return RDB_OK;
   if (!target || !sol || (!seed && chain->host.n_in > 0)) return fail(RDB_ERR_INVALID_ARG, "target, seed and sol are required");
   if (max_iter < 0 || !(toll >= 0.0)) return fail(RDB_ERR_INVALID_ARG, "max_iter and toll must be non-negative");
+  RDB_ENTER(chain);
   RDB_CUDA(launch_ik(*chain, n, ld, target, seed, q_min, q_max, weight, toll, max_iter, sol, status, iterations, error_norm,
                      (cudaStream_t)stream));
   return RDB_OK;
@@ -420,6 +469,7 @@ int32_t rdb_component_columns(int32_t type)
 rdb_status rdb_chain_set_components(rdb_chain* chain, int32_t n, const rdb_component_desc* components)
 {
   if (!chain || n < 0 || n > RDB_MAX_COMPONENTS || (n > 0 && !components)) return fail(RDB_ERR_INVALID_ARG, "bad component list");
+  RDB_LOCK(chain);
   ComponentsDev C{};
   for (int k = 0; k < n; k++)
   {
@@ -454,6 +504,7 @@ rdb_status rdb_components_regressor_batch(const rdb_chain* chain, const rdb_samp
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
   if (in->n == 0 || chain->comps.cols == 0) return RDB_OK;
   if (!phi_c || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "phi_c: null or ld_out < n");
   RDB_CUDA(launch_components_regressor(*chain, to_dev(in), phi_c, ld_out, (cudaStream_t)stream));
@@ -465,6 +516,7 @@ rdb_status rdb_components_torque_batch(const rdb_chain* chain, const rdb_samples
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
   if (in->n == 0) return RDB_OK;
   if (!torque || ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "torque: null or ld_out < n");
   if (chain->comps.cols > 0 && !parameters) return fail(RDB_ERR_INVALID_ARG, "parameters is null");
@@ -474,14 +526,16 @@ rdb_status rdb_components_torque_batch(const rdb_chain* chain, const rdb_samples
   return RDB_OK;
 }
 
-rdb_status rdb_regressor_gram_ext_batch(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+rdb_status rdb_regressor_gram_ext_batch(rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                         double* tau_sq, int32_t accumulate, void* stream)
 {
   rdb_status s = check_samples(chain, in, true);
   if (s != RDB_OK) return s;
+  RDB_ENTER(chain);
+  RDB_LOCK(chain);
   if (in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
   if (!gram || !rhs) return fail(RDB_ERR_INVALID_ARG, "gram / rhs must not be null");
-  RDB_CUDA(launch_gram(*const_cast<rdb_chain*>(chain), to_dev(in), tau_meas, gram, rhs, tau_sq, accumulate, (cudaStream_t)stream, true));
+  RDB_CUDA(launch_gram(*chain, to_dev(in), tau_meas, gram, rhs, tau_sq, accumulate, (cudaStream_t)stream, true));
   return RDB_OK;
 }
 
@@ -573,6 +627,7 @@ struct Plane
   double* h_out = nullptr;       // host destination (outputs)
   int64_t planes = 0;
   int64_t ld = 0;  // host plane stride
+  bool records = false;  // RDB_LAYOUT_EIGEN output: [sample][planes] dense records on both sides (one contiguous copy per chunk)
   double* d[2] = {nullptr, nullptr};
 };
 
@@ -623,8 +678,11 @@ struct HostPipe
   rdb_status d2h(Plane& p, int slot, int64_t off, int64_t len)
   {
     if (!p.h_out || p.planes == 0) return RDB_OK;
-    RDB_CUDA(cudaMemcpy2DAsync(p.h_out + off, p.ld * sizeof(double), p.d[slot], chunk * sizeof(double), len * sizeof(double), p.planes,
-                               cudaMemcpyDeviceToHost, st[slot]));
+    if (p.records)
+      RDB_CUDA(cudaMemcpyAsync(p.h_out + off * p.planes, p.d[slot], sizeof(double) * (size_t)len * p.planes, cudaMemcpyDeviceToHost, st[slot]));
+    else
+      RDB_CUDA(cudaMemcpy2DAsync(p.h_out + off, p.ld * sizeof(double), p.d[slot], chunk * sizeof(double), len * sizeof(double), p.planes,
+                                 cudaMemcpyDeviceToHost, st[slot]));
     return RDB_OK;
   }
   rdb_status finish()
@@ -665,16 +723,21 @@ struct HostIn
 
 extern "C" {
 
-rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out)
+rdb_status rdb_kinematics_batch_host(rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out)
 {
   RDB_TRY(check_samples(chain, in, true));
-  if (!out || out->ld < in->n) return fail(RDB_ERR_INVALID_ARG, "kinematics_out: need ld >= n");
+  RDB_ENTER(chain);
+  RDB_LOCK(chain);  // the staging arena and its streams live in the handle
+  if (!out || bad_layout(out->layout)) return fail(RDB_ERR_INVALID_ARG, "kinematics_out: null or unknown layout");
+  const bool eig = out->layout == RDB_LAYOUT_EIGEN;
+  if (!eig && out->ld < in->n) return fail(RDB_ERR_INVALID_ARG, "kinematics_out: need ld >= n");
   const int nL = chain->host.nj + 1, n_in = chain->host.n_in;
+  const int64_t pose = eig ? 16 : 12;  // doubles per pose: Affine3d image / 3x4 [R|p]
   HostIn hi;
   hi.bind(in, n_in);
   double* const outs[11] = {out->T_tool,        out->T_links, out->jacobian,    out->twist,          out->dtwist, out->dtwist_lin,
                             out->dtwist_nonlin, out->ddtwist, out->ddtwist_lin, out->ddtwist_nonlin, out->torque};
-  const int64_t rows[11] = {12, 12 * nL, 6 * n_in, 6 * nL, 6 * nL, 6 * nL, 6 * nL, 6 * nL, 6 * nL, 6 * nL, n_in};
+  const int64_t rows[11] = {pose, pose * nL, 6 * n_in, 6 * nL, 6 * nL, 6 * nL, 6 * nL, 6 * nL, 6 * nL, 6 * nL, n_in};
   Plane po[11];
   std::vector<Plane*> all = {&hi.q, &hi.dq, &hi.ddq, &hi.dddq};
   for (int k = 0; k < 11; k++)
@@ -682,10 +745,11 @@ rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* 
     po[k].h_out = outs[k];
     po[k].planes = outs[k] ? rows[k] : 0;
     po[k].ld = out->ld;
+    po[k].records = eig;
     all.push_back(&po[k]);
   }
   HostPipe pipe;
-  RDB_TRY(pipe.init(const_cast<rdb_chain*>(chain)->host_arena, in->n, 1 << 20, all));
+  RDB_TRY(pipe.init(chain->host_arena, in->n, 1 << 20, all));
   int slot = 0;
   for (int64_t off = 0; off < in->n; off += pipe.chunk, slot ^= 1)
   {
@@ -695,18 +759,23 @@ rdb_status rdb_kinematics_batch_host(const rdb_chain* chain, const rdb_samples* 
     RDB_TRY(pipe.h2d(hi.ddq, slot, off, len));
     RDB_TRY(pipe.h2d(hi.dddq, slot, off, len));
     rdb_samples v = hi.view(slot, len, pipe.chunk);
-    rdb_kinematics_out o{pipe.chunk,    po[0].d[slot], po[1].d[slot], po[2].d[slot], po[3].d[slot],  po[4].d[slot],
-                         po[5].d[slot], po[6].d[slot], po[7].d[slot], po[8].d[slot], po[9].d[slot], po[10].d[slot]};
+    rdb_kinematics_out o{pipe.chunk,    po[0].d[slot], po[1].d[slot], po[2].d[slot], po[3].d[slot], po[4].d[slot],
+                         po[5].d[slot], po[6].d[slot], po[7].d[slot], po[8].d[slot], po[9].d[slot], po[10].d[slot], out->layout};
     RDB_TRY(rdb_kinematics_batch(chain, &v, &o, pipe.st[slot]));
     for (int k = 0; k < 11; k++) RDB_TRY(pipe.d2h(po[k], slot, off, len));
   }
   return pipe.finish();
 }
 
-static rdb_status dyn_host(const rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, double* inertia, int64_t ld_out, int what)
+// what: 0 regressor (+ torque), 1 torque, 2 inertia, 3 rdb_dynamics_batch (any subset)
+static rdb_status dyn_host(rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, double* inertia, int64_t ld_out, int what,
+                           int32_t layout = RDB_LAYOUT_SOA)
 {
   RDB_TRY(check_samples(chain, in, true));
-  if (ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "ld_out < n");
+  RDB_ENTER(chain);
+  RDB_LOCK(chain);
+  const bool eig = layout == RDB_LAYOUT_EIGEN;
+  if (!eig && ld_out < in->n) return fail(RDB_ERR_INVALID_ARG, "ld_out < n");
   const int n_in = chain->host.n_in;
   HostIn hi;
   hi.bind(in, n_in);
@@ -714,8 +783,9 @@ static rdb_status dyn_host(const rdb_chain* chain, const rdb_samples* in, double
   pphi.h_out = phi; pphi.planes = phi ? (int64_t)10 * chain->host.nj * n_in : 0; pphi.ld = ld_out;
   ptau.h_out = torque; ptau.planes = torque ? n_in : 0; ptau.ld = ld_out;
   pM.h_out = inertia; pM.planes = inertia ? (int64_t)n_in * n_in : 0; pM.ld = ld_out;
+  pphi.records = ptau.records = pM.records = eig;
   HostPipe pipe;
-  RDB_TRY(pipe.init(const_cast<rdb_chain*>(chain)->host_arena, in->n, phi ? (1 << 18) : (1 << 21), {&hi.q, &hi.dq, &hi.ddq, &hi.dddq, &pphi, &ptau, &pM}));
+  RDB_TRY(pipe.init(chain->host_arena, in->n, phi ? (1 << 18) : (1 << 21), {&hi.q, &hi.dq, &hi.ddq, &hi.dddq, &pphi, &ptau, &pM}));
   int slot = 0;
   for (int64_t off = 0; off < in->n; off += pipe.chunk, slot ^= 1)
   {
@@ -727,6 +797,11 @@ static rdb_status dyn_host(const rdb_chain* chain, const rdb_samples* in, double
     if (what == 0) RDB_TRY(rdb_regressor_batch(chain, &v, pphi.d[slot], ptau.d[slot], pipe.chunk, pipe.st[slot]));
     if (what == 1) RDB_TRY(rdb_torque_batch(chain, &v, ptau.d[slot], pipe.chunk, pipe.st[slot]));
     if (what == 2) RDB_TRY(rdb_inertia_batch(chain, &v, pM.d[slot], pipe.chunk, pipe.st[slot]));
+    if (what == 3)
+    {
+      rdb_dynamics_out o{pipe.chunk, pphi.d[slot], ptau.d[slot], pM.d[slot], layout};
+      RDB_TRY(rdb_dynamics_batch(chain, &v, &o, pipe.st[slot]));
+    }
     RDB_TRY(pipe.d2h(pphi, slot, off, len));
     RDB_TRY(pipe.d2h(ptau, slot, off, len));
     RDB_TRY(pipe.d2h(pM, slot, off, len));
@@ -734,24 +809,32 @@ static rdb_status dyn_host(const rdb_chain* chain, const rdb_samples* in, double
   return pipe.finish();
 }
 
-rdb_status rdb_torque_batch_host(const rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out)
+rdb_status rdb_torque_batch_host(rdb_chain* chain, const rdb_samples* in, double* torque, int64_t ld_out)
 {
   if (!torque) return fail(RDB_ERR_INVALID_ARG, "torque is null");
   return dyn_host(chain, in, nullptr, torque, nullptr, ld_out, 1);
 }
-rdb_status rdb_regressor_batch_host(const rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, int64_t ld_out)
+rdb_status rdb_regressor_batch_host(rdb_chain* chain, const rdb_samples* in, double* phi, double* torque, int64_t ld_out)
 {
   if (!phi) return fail(RDB_ERR_INVALID_ARG, "phi is null");
   if (in && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
   return dyn_host(chain, in, phi, torque, nullptr, ld_out, 0);
 }
-rdb_status rdb_inertia_batch_host(const rdb_chain* chain, const rdb_samples* in, double* inertia, int64_t ld_out)
+rdb_status rdb_inertia_batch_host(rdb_chain* chain, const rdb_samples* in, double* inertia, int64_t ld_out)
 {
   if (!inertia) return fail(RDB_ERR_INVALID_ARG, "inertia is null");
   return dyn_host(chain, in, nullptr, nullptr, inertia, ld_out, 2);
 }
 
-rdb_status rdb_regressor_gram_batch_host(const rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
+rdb_status rdb_dynamics_batch_host(rdb_chain* chain, const rdb_samples* in, const rdb_dynamics_out* out)
+{
+  if (!out || bad_layout(out->layout)) return fail(RDB_ERR_INVALID_ARG, "dynamics_out: null or unknown layout");
+  if (out->regressor && in && in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
+  if (!out->regressor && !out->torque && !out->inertia) return RDB_OK;
+  return dyn_host(chain, in, out->regressor, out->torque, out->inertia, out->ld, 3, out->layout);
+}
+
+rdb_status rdb_regressor_gram_batch_host(rdb_chain* chain, const rdb_samples* in, const double* tau_meas, double* gram, double* rhs,
                                          double* tau_sq, int32_t accumulate)
 {
   // Streaming pipeline kept in the handle (streams, 3 staging slots, events): H2D of chunk k+1/k+2 on the copy
@@ -760,11 +843,18 @@ rdb_status rdb_regressor_gram_batch_host(const rdb_chain* chain, const rdb_sampl
   RDB_TRY(check_samples(chain, in, true));
   if (in->n > 0 && (!in->dq || !in->ddq)) return fail(RDB_ERR_DIM_MISMATCH, "Input data dimensions mismatch");
   if (!gram || !rhs) return fail(RDB_ERR_INVALID_ARG, "gram / rhs must not be null");
-  rdb_chain* ch = const_cast<rdb_chain*>(chain);
+  RDB_ENTER(chain);
+  RDB_LOCK(chain);  // streams, staging slots and events of the pipeline live in the handle
+  rdb_chain* ch = chain;
   GramHostPipe& hp = ch->gram_host;
   const int n_in = ch->host.n_in, P = 10 * ch->host.nj;
   // chunk: measured on B200 (C6, 4 M samples per call, pinned inputs): 2^16 354, 2^17 330, 2^18 375, 2^19 372 M samples/s end to end
-  static const int64_t chunk = [] { const char* e = getenv("RDB_HOST_CHUNK"); return e ? (int64_t)atoll(e) : (int64_t)(1 << 18); }();
+  // RDB_HOST_CHUNK (samples per staged chunk) is a tuning knob only -- it never changes results; clamped to [2^10, 2^24]
+  static const int64_t chunk = [] {
+    const char* e = getenv("RDB_HOST_CHUNK");
+    const int64_t v = e ? (int64_t)atoll(e) : (int64_t)(1 << 18);
+    return std::min<int64_t>(std::max<int64_t>(v, 1 << 10), 1 << 24);
+  }();
   const size_t n_out = (size_t)P * P + P + 1;
   if (!hp.copy)
   {

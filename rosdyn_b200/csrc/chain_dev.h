@@ -70,6 +70,16 @@ struct KinOutDev
 {
   int64_t ld;
   double *T_tool, *T_links, *jacobian, *twist, *dtwist, *dtwist_lin, *dtwist_nonlin, *ddtwist, *ddtwist_lin, *ddtwist_nonlin, *torque;
+  int32_t eigen;  // RDB_LAYOUT_EIGEN: per-sample records laid out as the reference's Eigen objects (see rosdyn_b200.h)
 };
+
+// outputs of the link-frame walker.  Element (plane p, sample i) of an array lives at  base + p * ps + i * ss_<array>:
+// SoA planes: ps = ld, ss = 1;  Eigen records: ps = 1, ss = planes of the array (the record is the column-major Eigen matrix)
+struct DynOutDev
+{
+  double *phi, *tau, *M;
+  int64_t ps, ss_phi, ss_tau, ss_M;
+};
+inline DynOutDev dyn_out_soa(double* phi, double* tau, double* M, int64_t ld) { return DynOutDev{phi, tau, M, ld, 1, 1, 1}; }
 
 }  // namespace rdb

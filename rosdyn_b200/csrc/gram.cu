@@ -176,8 +176,13 @@ cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_m
     return cudaGetLastError();
   }
   {
-    // fused warp-specialised kernel (gram_fused.cu) whenever the chain fits it; RDB_GRAM_IMPL=v0 forces the general pipeline
+    // fused warp-specialised kernel (gram_fused.cu) whenever the chain fits it.  Development builds (-DRDB_DEV_SWITCHES, never the shipped
+    // library) can force the general pipeline with RDB_GRAM_IMPL=v0
+#ifdef RDB_DEV_SWITCHES
     static const bool force_v0 = [] { const char* e = getenv("RDB_GRAM_IMPL"); return e && e[0] == 'v'; }();
+#else
+    constexpr bool force_v0 = false;
+#endif
     if (!force_v0)
     {
       cudaError_t e = (P == Pr) ? launch_gram_fused(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st)

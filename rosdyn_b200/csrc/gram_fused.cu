@@ -738,6 +738,18 @@ __global__ void gram_fold_expand_kernel(const double* __restrict__ T, const int3
   if (a != b) gram[(size_t)a * P + b] = v;
 }
 
+// Timing experiments (1: skip the generation, 2: skip the MMA) exist in development builds only (-DRDB_DEV_SWITCHES); the shipped library
+// always computes.
+static int gram_dev_switch()
+{
+#ifdef RDB_DEV_SWITCHES
+  static const int dbg = [] { const char* e = getenv("RDB_GRAM_DEBUG"); return e ? atoi(e) : 0; }();
+  return dbg;
+#else
+  return 0;
+#endif
+}
+
 template <int NJ>
 static ChainDev<NJ> narrow_g(const ChainDev<RDB_MAX_JOINTS>& h)
 {
@@ -774,7 +786,7 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const do
     cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS, REV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  static const int dbg = [] { const char* e = getenv("RDB_GRAM_DEBUG"); return e ? atoi(e) : 0; }();  // 1: skip generation, 2: skip MMA (timing experiments only)
+  const int dbg = gram_dev_switch();
   const int64_t ngroups = (in.n + 31) / 32;
   const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + SLOTS - 1) / SLOTS);
   {
@@ -922,7 +934,7 @@ static cudaError_t launch_cross_nj(ChainHost& ch, const GramComps& gc, const Sam
   if (e != cudaSuccess) return e;
   const int64_t ngroups = (in.n + 31) / 32;
   const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + SLOTS - 1) / SLOTS);
-  static const int dbg = [] { const char* e = getenv("RDB_GRAM_DEBUG"); return e ? atoi(e) : 0; }();  // timing experiments only
+  const int dbg = gram_dev_switch();
   gram_fused_kernel<NJ, SLOTS, REV, 1><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), gc, in, tau_meas, xpartial, dbg);
   count_launch();
   gram_cross_reduce_kernel<<<(G::NXT * 64 + 255) / 256, 256, 0, st>>>(xpartial, grid, G::NXT * 64, xsum);

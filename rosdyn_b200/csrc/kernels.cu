@@ -57,9 +57,13 @@ enum : int
 // REV (unrolled torque / inertia kernels on the folded chain): every joint is revolute, so the joint type is a compile-time fact -- no type
 // selects and the linear half of the joint screws (an exact zero) is never multiplied
 template <int NJ_T, int MODE, bool REV = false, class ChainT>
-__device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, double* __restrict__ phi, double* __restrict__ tau_out,
-                                         double* __restrict__ M_out, int64_t ld_out, int64_t i)
+__device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, const DynOutDev& out, int64_t i)
 {
+  // element (plane p, sample i) of an output array: base + p * ld_out + i * ss (SoA planes: ld_out = ld, ss = 1; Eigen records: ld_out = 1)
+  double* __restrict__ const phi = out.phi + i * out.ss_phi;
+  double* __restrict__ const tau_out = out.tau;
+  double* __restrict__ const M_out = out.M;
+  const int64_t ld_out = out.ps, i_tau = i * out.ss_tau, i_M = i * out.ss_M;
   constexpr int CAP = Cap<NJ_T>::value;
   const int nj = NJ_T > 0 ? NJ_T : C.nj;
   const int n_in = C.n_in;
@@ -229,7 +233,7 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
         }
         if (r >= 0)
         {
-          double* o = phi + (colbase + r) * ld_out + i;
+          double* o = phi + (colbase + r) * ld_out;
           const int64_t st = (int64_t)n_in * ld_out;
           __stcs(o, e0);
           __stcs(o + st, h.x);
@@ -250,7 +254,7 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
         const int r = C.joint[j].in;
         if (r >= 0)
         {
-          double* o = phi + (colbase + r) * ld_out + i;
+          double* o = phi + (colbase + r) * ld_out;
           const int64_t st = (int64_t)n_in * ld_out;
 #pragma unroll
           for (int p = 0; p < 10; p++) __stcs(o + p * st, 0.0);
@@ -303,7 +307,7 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
     for (int j = 0; j < (NJ_T > 0 ? NJ_T : nj); j++)
     {
       const int r = C.joint[j].in;
-      if (r >= 0) st_out(tau_out, r, ld_out, i, tau[j]);
+      if (r >= 0) st_out(tau_out, r, ld_out, i_tau, tau[j]);
     }
   }
   if (kInr)
@@ -317,30 +321,28 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
         if (rj >= 0 && rk >= 0)
         {
           const double m = M[j * (j + 1) / 2 + k];
-          st_out(M_out, (int64_t)rj * n_in + rk, ld_out, i, m);
-          if (j != k) st_out(M_out, (int64_t)rk * n_in + rj, ld_out, i, m);
+          st_out(M_out, (int64_t)rj * n_in + rk, ld_out, i_M, m);
+          if (j != k) st_out(M_out, (int64_t)rk * n_in + rj, ld_out, i_M, m);
         }
       }
   }
 }
 
 template <int NJ, int MODE, bool REV = false>
-__global__ void __launch_bounds__(RDB_BLOCK, (MODE & DYN_REGRESSOR) ? RDB_REG_MINB : RDB_DYN_MINB) dyn_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, double* __restrict__ phi,
-                                                        double* __restrict__ tau, double* __restrict__ M, int64_t ld_out)
+__global__ void __launch_bounds__(RDB_BLOCK, (MODE & DYN_REGRESSOR) ? RDB_REG_MINB : RDB_DYN_MINB) dyn_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const DynOutDev out)
 {
   const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
   if (i >= in.n) return;
-  dyn_body<NJ, MODE, REV>(C, in, phi, tau, M, ld_out, i);
+  dyn_body<NJ, MODE, REV>(C, in, out, i);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(RDB_BLOCK) dyn_kernel_generic(const ChainDev<RDB_MAX_JOINTS>* __restrict__ C, const SamplesDev in,
-                                                                double* __restrict__ phi, double* __restrict__ tau, double* __restrict__ M,
-                                                                int64_t ld_out)
+                                                                const DynOutDev out)
 {
   const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
   if (i >= in.n) return;
-  dyn_body<0, MODE>(*C, in, phi, tau, M, ld_out, i);
+  dyn_body<0, MODE>(*C, in, out, i);
 }
 
 // =============================================================================================================
@@ -377,6 +379,24 @@ __device__ __forceinline__ void st_pose(double* p, int64_t plane0, int64_t ld, i
     __stcs(p + (plane0 + 4 * r + 2) * ld + i, R[3 * r + 2]);
     __stcs(p + (plane0 + 4 * r + 3) * ld + i, r == 0 ? t.x : (r == 1 ? t.y : t.z));
   }
+}
+
+// the same pose as an Eigen::Affine3d image (internal/types.h:137): 4x4 column-major, 16 contiguous doubles with the [0 0 0 1] row; `p` points at
+// the sample's record
+__device__ __forceinline__ void st_pose_eigen(double* p, const double* R, V3 t)
+{
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+  {
+    __stcs(p + 4 * c + 0, R[c]);
+    __stcs(p + 4 * c + 1, R[3 + c]);
+    __stcs(p + 4 * c + 2, R[6 + c]);
+    __stcs(p + 4 * c + 3, 0.0);
+  }
+  __stcs(p + 12, t.x);
+  __stcs(p + 13, t.y);
+  __stcs(p + 14, t.z);
+  __stcs(p + 15, 1.0);
 }
 
 // Per-joint state of the base-frame walker that must outlive the walk: the base-frame axis and the origin of every joint (the Jacobian needs
@@ -440,7 +460,13 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
   constexpr int CAP = Cap<NJ_T>::value;
   const int nj = NJ_T > 0 ? NJ_T : C.nj;
   const int n_in = C.n_in;
-  const int64_t ld = o.ld;
+  // element (plane p, sample i) of an output array: base + p * ld + i * ss.  SoA planes: ld = o.ld, ss = 1.  Eigen records (o.eigen): ld = 1
+  // and ss = planes of the array, i.e. every sample owns a dense record laid out as the reference's Eigen object (6-vectors of all links back to
+  // back = VectorOfVector6d, Jacobian 6 x n_act column-major); poses become 16-double Affine3d images (st_pose_eigen)
+  const bool eig = o.eigen != 0;
+  const int64_t ld = eig ? 1 : o.ld;
+  const int64_t i_tw = eig ? i * (6 * (nj + 1)) : i, i_jac = eig ? i * (6 * n_in) : i, i_tau = eig ? i * n_in : i;
+  double* const Tl_e = o.T_links + i * (16 * (nj + 1));  // Eigen records of the link poses (used when eig)
 
   constexpr bool cJer = (MASK & (K_DDTWIST | K_DDTWIST_NONLIN)) != 0;
   constexpr bool cAcc = (MASK & (K_DTWIST | K_TORQUE)) != 0 || cJer;
@@ -490,14 +516,18 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     if ((MASK & (K_DDTWIST | K_DDTWIST_LIN)) != 0) dddq_nx = ld_in(in.dddq, in0, in.ld, i);
   }
   // link 0 = base: identity pose, zero twists (primitives_impl.h:661-677, 697)
-  if (wTl) st_pose(o.T_links, 0, ld, i, R, p);
-  if (wV) st_tw(o.twist, 0, ld, i, v);
-  if (wA) st_tw(o.dtwist, 0, ld, i, v);
-  if (wAl) st_tw(o.dtwist_lin, 0, ld, i, v);
-  if (wAn) st_tw(o.dtwist_nonlin, 0, ld, i, v);
-  if (wJ) st_tw(o.ddtwist, 0, ld, i, v);
-  if (wJl) st_tw(o.ddtwist_lin, 0, ld, i, v);
-  if (wJn) st_tw(o.ddtwist_nonlin, 0, ld, i, v);
+  if (wTl)
+  {
+    if (eig) st_pose_eigen(Tl_e, R, p);
+    else st_pose(o.T_links, 0, ld, i, R, p);
+  }
+  if (wV) st_tw(o.twist, 0, ld, i_tw, v);
+  if (wA) st_tw(o.dtwist, 0, ld, i_tw, v);
+  if (wAl) st_tw(o.dtwist_lin, 0, ld, i_tw, v);
+  if (wAn) st_tw(o.dtwist_nonlin, 0, ld, i_tw, v);
+  if (wJ) st_tw(o.ddtwist, 0, ld, i_tw, v);
+  if (wJl) st_tw(o.ddtwist_lin, 0, ld, i_tw, v);
+  if (wJn) st_tw(o.ddtwist_nonlin, 0, ld, i_tw, v);
 
 #pragma unroll
   for (int l = 0; l < (NJ_T > 0 ? NJ_T : nj); l++)
@@ -523,7 +553,11 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     mul33(R, Rpc, Rn);
 #pragma unroll
     for (int k = 0; k < 9; k++) R[k] = Rn[k];
-    if (wTl) st_pose(o.T_links, (int64_t)12 * (l + 1), ld, i, R, p);
+    if (wTl)
+    {
+      if (eig) st_pose_eigen(Tl_e + 16 * (l + 1), R, p);
+      else st_pose(o.T_links, (int64_t)12 * (l + 1), ld, i, R, p);
+    }
 
     if (cJac) js.set(l, axb, p);
 
@@ -556,27 +590,27 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     {
       v = tw_axpy_s<NP>(transl(v, d), s, dql);  // primitives_impl.h:1007-1008
       vxs = NP ? Tw{cross(v.l, s.a), cross(v.a, s.a)} : scross(v, s);
-      if (wV) st_tw(o.twist, l + 1, ld, i, v);
+      if (wV) st_tw(o.twist, l + 1, ld, i_tw, v);
     }
     if (MASK & K_DTWIST_LIN)
     {
       al = tw_axpy_s<NP>(transl(al, d), s, ddql);  // primitives_impl.h:1055-1056
-      if (wAl) st_tw(o.dtwist_lin, l + 1, ld, i, al);
+      if (wAl) st_tw(o.dtwist_lin, l + 1, ld, i_tw, al);
     }
     if (MASK & K_DTWIST_NONLIN)
     {
       an = tw_axpy(transl(an, d), vxs, dql);  // primitives_impl.h:1074-1075
-      if (wAn) st_tw(o.dtwist_nonlin, l + 1, ld, i, an);
+      if (wAn) st_tw(o.dtwist_nonlin, l + 1, ld, i_tw, an);
     }
     if (cAcc)
     {
       a = tw_axpy_s<NP>(tw_axpy(transl(a, d), vxs, dql), s, ddql);  // primitives_impl.h:1116-1117
-      if (wA) st_tw(o.dtwist, l + 1, ld, i, a);
+      if (wA) st_tw(o.dtwist, l + 1, ld, i_tw, a);
     }
     if (MASK & K_DDTWIST_LIN)
     {
       jl = tw_axpy_s<NP>(transl(jl, d), s, dddql);  // primitives_impl.h:1148-1149
-      if (wJl) st_tw(o.ddtwist_lin, l + 1, ld, i, jl);
+      if (wJl) st_tw(o.ddtwist_lin, l + 1, ld, i_tw, jl);
     }
     if (cJer)
     {
@@ -587,12 +621,12 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
       if (MASK & K_DDTWIST)
       {
         jf = tw_axpy(tw_axpy(tw_axpy_s<NP>(transl(jf, d), s, dddql), vxs, ddql), k, dql);
-        if (wJ) st_tw(o.ddtwist, l + 1, ld, i, jf);
+        if (wJ) st_tw(o.ddtwist, l + 1, ld, i_tw, jf);
       }
       if (MASK & K_DDTWIST_NONLIN)
       {
         jn = tw_axpy(tw_axpy(transl(jn, d), vxs, ddql), k, dql);
-        if (wJn) st_tw(o.ddtwist_nonlin, l + 1, ld, i, jn);
+        if (wJn) st_tw(o.ddtwist_nonlin, l + 1, ld, i_tw, jn);
       }
     }
 
@@ -628,7 +662,11 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     }
   }
 
-  if ((MASK & K_TTOOL) && o.T_tool) st_pose(o.T_tool, 0, ld, i, R, p);
+  if ((MASK & K_TTOOL) && o.T_tool)
+  {
+    if (eig) st_pose_eigen(o.T_tool + i * 16, R, p);
+    else st_pose(o.T_tool, 0, ld, i, R, p);
+  }
 
   if ((MASK & K_JAC) && o.jacobian)
   {
@@ -643,8 +681,8 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
         const V3 z = v3(0, 0, 0);
         const V3 abj = js.ab(j);
         const V3 lin = tj == RDB_JOINT_REVOLUTE ? cross(abj, p - js.pj(j)) : ((!NP && tj == RDB_JOINT_PRISMATIC) ? abj : z);
-        st3(o.jacobian, (int64_t)6 * r, ld, i, lin);
-        st3(o.jacobian, (int64_t)6 * r + 3, ld, i, tj == RDB_JOINT_REVOLUTE ? abj : z);
+        st3(o.jacobian, (int64_t)6 * r, ld, i_jac, lin);
+        st3(o.jacobian, (int64_t)6 * r + 3, ld, i_jac, tj == RDB_JOINT_REVOLUTE ? abj : z);
       }
     }
   }
@@ -654,7 +692,7 @@ __device__ __forceinline__ void kin_body(const ChainT& C, const SamplesDev& in, 
     for (int j = 0; j < (NJ_T > 0 ? NJ_T : nj); j++)
     {
       const int r = C.joint[j].in;
-      if (r >= 0) st_out(o.torque, r, ld, i, tau[j]);
+      if (r >= 0) st_out(o.torque, r, ld, i_tau, tau[j]);
     }
   }
   (void)n_in;
@@ -728,8 +766,7 @@ static inline unsigned grid_for(int64_t n) { return (unsigned)((n + RDB_BLOCK - 
 #define RDB_FAST_NJ(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 
 template <int MODE>
-static cudaError_t launch_dyn_mode(const ChainHost& ch, const SamplesDev& in, double* phi, double* tau, double* M, int64_t ld_out,
-                                   cudaStream_t st)
+static cudaError_t launch_dyn_mode(const ChainHost& ch, const SamplesDev& in, const DynOutDev& out, cudaStream_t st)
 {
   if (in.n <= 0) return cudaSuccess;
   const unsigned grid = grid_for(in.n);
@@ -744,30 +781,34 @@ static cudaError_t launch_dyn_mode(const ChainHost& ch, const SamplesDev& in, do
 #define X(N)                                                                                                                    \
   case N:                                                                                                                       \
     if ((MODE & DYN_REGRESSOR) == 0 && rev)                                                                                     \
-      dyn_kernel<N, (MODE & DYN_REGRESSOR) ? 0 : MODE, true><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(H), in, phi, tau, M, ld_out); \
+      dyn_kernel<N, (MODE & DYN_REGRESSOR) ? 0 : MODE, true><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(H), in, out);        \
     else                                                                                                                        \
-      dyn_kernel<N, MODE><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(H), in, phi, tau, M, ld_out);                                   \
+      dyn_kernel<N, MODE><<<grid, RDB_BLOCK, 0, st>>>(narrow<N>(H), in, out);                                                      \
     break;
     RDB_FAST_NJ(X)
 #undef X
     default:
-      dyn_kernel_generic<MODE><<<grid, RDB_BLOCK, 0, st>>>(ch.dev, in, phi, tau, M, ld_out);
+      dyn_kernel_generic<MODE><<<grid, RDB_BLOCK, 0, st>>>(ch.dev, in, out);
   }
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_dyn(const ChainHost& ch, int mode, const SamplesDev& in, double* phi, double* tau, double* M, int64_t ld_out,
-                       cudaStream_t st)
+cudaError_t launch_dyn(const ChainHost& ch, int mode, const SamplesDev& in, const DynOutDev& out, cudaStream_t st)
 {
   switch (mode)
   {
-    case DYN_REGRESSOR: return launch_dyn_mode<DYN_REGRESSOR>(ch, in, phi, tau, M, ld_out, st);
-    case DYN_REGRESSOR | DYN_TORQUE: return launch_dyn_mode<DYN_REGRESSOR | DYN_TORQUE>(ch, in, phi, tau, M, ld_out, st);
-    case DYN_TORQUE: return launch_dyn_mode<DYN_TORQUE>(ch, in, phi, tau, M, ld_out, st);
-    case DYN_INERTIA: return launch_dyn_mode<DYN_INERTIA>(ch, in, phi, tau, M, ld_out, st);
+    case DYN_REGRESSOR: return launch_dyn_mode<DYN_REGRESSOR>(ch, in, out, st);
+    case DYN_REGRESSOR | DYN_TORQUE: return launch_dyn_mode<DYN_REGRESSOR | DYN_TORQUE>(ch, in, out, st);
+    case DYN_TORQUE: return launch_dyn_mode<DYN_TORQUE>(ch, in, out, st);
+    case DYN_INERTIA: return launch_dyn_mode<DYN_INERTIA>(ch, in, out, st);
   }
   return cudaErrorInvalidValue;
+}
+cudaError_t launch_dyn(const ChainHost& ch, int mode, const SamplesDev& in, double* phi, double* tau, double* M, int64_t ld_out,
+                       cudaStream_t st)
+{
+  return launch_dyn(ch, mode, in, dyn_out_soa(phi, tau, M, ld_out), st);
 }
 
 template <unsigned MASK>

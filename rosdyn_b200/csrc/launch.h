@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "chain_dev.h"
 
@@ -76,6 +77,32 @@ struct ChainHost
   HostArena host_arena;
   int sm_count = 148;
   uint64_t model_version = 0;  // bumped by every upload of the model (creation, rdb_chain_set_input_joints)
+  // serialises the entries that touch the handle's mutable state (model upload, Gram workspaces, the staging pipelines of the *_host entries):
+  // two host threads may share one handle -- their calls run one after the other instead of racing
+  std::recursive_mutex mu;
+};
+
+// RAII: make the handle's device current for the duration of an entry point and restore the caller's device afterwards
+struct DeviceScope
+{
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceScope(int device)
+  {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device)
+    {
+      err = cudaSetDevice(device);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~DeviceScope()
+  {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
 };
 
 extern std::atomic<uint64_t> g_launches;
@@ -83,6 +110,7 @@ inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed);
 
 cudaError_t launch_dyn(const ChainHost& ch, int mode, const SamplesDev& in, double* phi, double* tau, double* M, int64_t ld_out,
                        cudaStream_t st);
+cudaError_t launch_dyn(const ChainHost& ch, int mode, const SamplesDev& in, const DynOutDev& out, cudaStream_t st);
 cudaError_t launch_kin(const ChainHost& ch, unsigned want, const SamplesDev& in, const KinOutDev& o, cudaStream_t st);
 cudaError_t launch_fill_uniform(double* x, int n_planes, int64_t n, int64_t ld, uint64_t seed, int stream_id, cudaStream_t st);
 void fill_uniform_host(double* x, int n_planes, int64_t n, int64_t ld, uint64_t seed, int stream_id);

@@ -6,6 +6,7 @@
 // Host code on purpose: G is (10 nJ + Pc)^2 <= a few hundred squared, microseconds of work next to billions of samples.
 #include <algorithm>
 #include <cmath>
+#include <new>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -110,36 +111,58 @@ extern "C" rdb_status rdb_normal_equations_solve(int32_t P, const double* gram, 
 extern "C" rdb_status rdb_multiplicity(int32_t n, const int32_t* joint_type_of_input, const double* q, const double* q_min, const double* q_max,
                                        double* out, int64_t capacity, int64_t* count)
 {
-  if (n < 0 || !count || (n > 0 && (!joint_type_of_input || !q || !q_min || !q_max))) return RDB_ERR_INVALID_ARG;
+  if (n < 0 || !count || (n > 0 && (!joint_type_of_input || !q || !q_min || !q_max)))
+    return rdb::set_error(RDB_ERR_INVALID_ARG, "multiplicity: null or negative argument");
+  *count = 0;
   const double two_pi = 2.0 * 3.14159265358979323846;  // 2*M_PI
-  // the reference loops until the limit is passed; with its "no limit" defaults (+-1e10, PI.h:92-93) that is 1.6e9 turns per joint and an
-  // exponential number of vectors -- refuse limits wider than 10^3 turns instead of reproducing that
-  for (int i = 0; i < n; i++)
-    if (joint_type_of_input[i] == RDB_JOINT_REVOLUTE && !((q_max[i] - q_min[i]) <= 1.0e3 * two_pi)) return RDB_ERR_INVALID_ARG;
-  std::vector<std::vector<double>> ax((size_t)n);
+  // The reference loops until the limit is passed; with its "no limit" defaults (+-1e10, PI.h:92-93) that is 1.6e9 turns per joint and an
+  // exponential number of vectors.  Refused instead of reproduced: non-finite values (a NaN q never passes a limit), a revolute joint whose
+  // images number more than 2001 (limits wider than 10^3 turns, or q that far outside them), more than 2^22 vectors in total.
+  constexpr double MAX_TURNS = 1.0e3;
+  constexpr double MAX_TOTAL = 4194304.0;
+  double total = 1.0;
   for (int i = 0; i < n; i++)
   {
-    ax[i].push_back(q[i]);
+    if (!std::isfinite(q[i])) return rdb::set_error(RDB_ERR_INVALID_ARG, "multiplicity: q is not finite");
     if (joint_type_of_input[i] != RDB_JOINT_REVOLUTE) continue;
-    for (double t = q[i] + two_pi; !(t > q_max[i]); t += two_pi) ax[i].push_back(t);  // while (true) { tmp += 2 pi; if (tmp > max) break; ... }
-    for (double t = q[i] - two_pi; !(t < q_min[i]); t -= two_pi) ax[i].push_back(t);
+    if (!std::isfinite(q_min[i]) || !std::isfinite(q_max[i])) return rdb::set_error(RDB_ERR_INVALID_ARG, "multiplicity: limits are not finite");
+    const double up = std::max(0.0, (q_max[i] - q[i]) / two_pi), down = std::max(0.0, (q[i] - q_min[i]) / two_pi);
+    if (!(up <= MAX_TURNS) || !(down <= MAX_TURNS))
+      return rdb::set_error(RDB_ERR_INVALID_ARG, "multiplicity: more than 1000 turns between q and a joint limit");
+    total *= 1.0 + std::floor(up) + std::floor(down);
+    if (total > MAX_TOTAL) return rdb::set_error(RDB_ERR_INVALID_ARG, "multiplicity: more than 2^22 joint vectors");
   }
-  std::vector<std::vector<double>> all;
-  all.emplace_back(q, q + n);
-  for (int i = 0; i < n; i++)
+  try
   {
-    const size_t have = all.size();
-    for (size_t is = 1; is < ax[i].size(); is++)
-      for (size_t im = 0; im < have; im++)
-      {
-        std::vector<double> v = all[im];
-        v[i] = ax[i][is];
-        all.push_back(std::move(v));
-      }
+    std::vector<std::vector<double>> ax((size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+      ax[i].push_back(q[i]);
+      if (joint_type_of_input[i] != RDB_JOINT_REVOLUTE) continue;
+      for (double t = q[i] + two_pi; !(t > q_max[i]); t += two_pi) ax[i].push_back(t);  // while (true) { tmp += 2 pi; if (tmp > max) break; ... }
+      for (double t = q[i] - two_pi; !(t < q_min[i]); t -= two_pi) ax[i].push_back(t);
+    }
+    std::vector<std::vector<double>> all;
+    all.emplace_back(q, q + n);
+    for (int i = 0; i < n; i++)
+    {
+      const size_t have = all.size();
+      for (size_t is = 1; is < ax[i].size(); is++)
+        for (size_t im = 0; im < have; im++)
+        {
+          std::vector<double> v = all[im];
+          v[i] = ax[i][is];
+          all.push_back(std::move(v));
+        }
+    }
+    *count = (int64_t)all.size();
+    if (!out || capacity < *count) return rdb::set_error(RDB_ERR_INVALID_ARG, "multiplicity: capacity too small (count is set)");
+    for (size_t k = 0; k < all.size(); k++)
+      for (int i = 0; i < n; i++) out[k * (size_t)n + i] = all[k][i];
   }
-  *count = (int64_t)all.size();
-  if (!out || capacity < *count) return RDB_ERR_INVALID_ARG;
-  for (size_t k = 0; k < all.size(); k++)
-    for (int i = 0; i < n; i++) out[k * (size_t)n + i] = all[k][i];
+  catch (const std::bad_alloc&)  // nothing may cross the extern "C" boundary
+  {
+    return rdb::set_error(RDB_ERR_ALLOC, "multiplicity: out of host memory");
+  }
   return RDB_OK;
 }

@@ -107,8 +107,23 @@ private:
     while (name_char(*p_)) p_++;
     return std::string(b, p_);
   }
+  // nesting is bounded: the reader recurses once per level and a hostile document must not overflow the stack (a URDF nests 5 deep)
+  static constexpr int MAX_DEPTH = 256;
+  int depth_ = 0;
+  struct DepthGuard
+  {
+    int& d;
+    explicit DepthGuard(int& x) : d(x) { d++; }
+    ~DepthGuard() { d--; }
+  };
   std::unique_ptr<XmlNode> element(std::string& err)
   {
+    DepthGuard guard(depth_);
+    if (depth_ > MAX_DEPTH)
+    {
+      err = "elements nested deeper than 256 levels";
+      return nullptr;
+    }
     p_++;  // '<'
     std::unique_ptr<XmlNode> n(new XmlNode);
     n->name = name();

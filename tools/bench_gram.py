@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Dev tool: times the fused Gram entry (device-resident inputs) for C6 and C7; RDB_LIB_PATH selects a variant library,
-RDB_GRAM_DEBUG=1|2 skips generation | MMA (timing experiments only).   python tools/bench_gram.py [S] [steps]"""
+"""Dev tool: times the fused Gram entry (device-resident inputs) for C6 and C7.   python tools/bench_gram.py [S] [steps] [--lib path]
+--lib selects an experimental build (tools/build_variant.sh); builds made with -DRDB_DEV_SWITCHES honour RDB_GRAM_DEBUG=1|2
+(skip generation | MMA: timing experiments only -- the shipped library has no such switch)."""
 import os
 import sys
 
@@ -8,7 +9,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from rosdyn_b200 import fixtures  # noqa: E402
+from rosdyn_b200 import _lib, fixtures  # noqa: E402
+
+LIB = "default"
+if "--lib" in sys.argv:
+    k = sys.argv.index("--lib")
+    LIB = sys.argv[k + 1]
+    _lib.set_library_path(os.path.abspath(LIB))
+    del sys.argv[k:k + 2]
 from rosdyn_b200.chain import Chain, fill_uniform  # noqa: E402
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 8_000_000
@@ -28,5 +36,5 @@ for name, flop in (("c6", 30660), ("c7", 35770)):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    print(f"{os.environ.get('RDB_LIB_PATH', 'default'):40s} dbg={os.environ.get('RDB_GRAM_DEBUG', '0')} {name}: {ms:8.3f} ms  "
+    print(f"{LIB:40s} dbg={os.environ.get('RDB_GRAM_DEBUG', '0')} {name}: {ms:8.3f} ms  "
           f"{S / ms / 1e6:7.4f} G samples/s  {S * flop / ms / 1e9:6.2f} TFLOP/s (algorithmic)", flush=True)
