@@ -2,6 +2,7 @@
 // Mirrors the shape of the reference's smoke loops (rosdyn_core/test/test.cpp:108-187: every getter on random
 // inputs) but, unlike them, asserts: the algebraic invariants of SURVEY.md section 4 and the UR10 zero-pose answer.
 // Build: tools/build_facade.py (g++ only, links librosdyn_b200.so).  Needs a CUDA device to run.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -138,6 +139,37 @@ int main()
     scale = std::fmax(scale, std::fabs(b[r]));
   }
   CHECK(worst <= 1e-9 * scale, "G pi_nom == b: %g (scale %g)", worst, scale);
+  // latency of the per-sample getters (N = 1 batches: one launch + one synchronisation each), next to the reference's published per-call
+  // figures on a CPU core (reference README.md:29-45): the facade is a drop-in for signatures, the speed-up exists only for batches
+  {
+    VectorXd q1(6, 0.3), d1(6, 0.1), dd1(6, -0.2);
+    struct Row { const char* name; double ref_us; int which; };
+    const Row rows[] = {{"getTransformation", 0.7597, 0}, {"getJacobian", 1.0656, 1}, {"getJointTorque", 3.7673, 2}, {"getRegressor", -1.0, 3},
+                        {"getJointInertia", 10.0676, 4}};
+    for (const Row& r : rows)
+    {
+      const int reps = 2000;
+      for (int pass = 0; pass < 2; pass++)
+      {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int k = 0; k < reps; k++)
+        {
+          q1[0] = 0.3 + 1e-6 * k;
+          if (r.which == 0) chain.getTransformation(q1);
+          else if (r.which == 1) chain.getJacobian(q1);
+          else if (r.which == 2) chain.getJointTorque(q1, d1, dd1);
+          else if (r.which == 3) chain.getRegressor(q1, d1, dd1);
+          else chain.getJointInertia(q1);
+        }
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+        if (pass == 1)
+        {
+          if (r.ref_us > 0) std::printf("latency %-18s %8.2f us per call (N = 1)   reference (CPU core, README.md:29-45): %6.2f us\n", r.name, us, r.ref_us);
+          else std::printf("latency %-18s %8.2f us per call (N = 1)   reference: not published\n", r.name, us);
+        }
+      }
+    }
+  }
   std::printf("facade_check: %s (kernels launched: %llu)\n", g_fail ? "FAILED" : "ok", (unsigned long long)rdb_kernel_launch_count());
   return g_fail ? 1 : 0;
 }

@@ -349,3 +349,16 @@ def test_cpp_facade(torch, tmp_path):
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "rosdyn_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):   # per-call latency of the N = 1 getters (kept as evidence: profiles/r02_latency.txt)
+        open(os.path.join(out, "r02_latency.txt"), "w").write(r.stdout)
+
+
+def test_cpp_eigen_overloads(torch, tmp_path):
+    """The Eigen-typed overloads of chain.hpp (the reference's signatures), compiled against the Eigen subset of oracle/shim, run on the GPU:
+    Phi pi = tau, M ddq + h = tau, J dq = v_tool on the Eigen objects, and the batched Eigen-record sibling."""
+    import subprocess
+    from test_cpp_headers import build_eigen_facade
+    exe = build_eigen_facade(str(tmp_path / "eigen_facade"))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "eigen facade ok" in r.stdout, r.stdout + r.stderr
