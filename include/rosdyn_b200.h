@@ -327,8 +327,8 @@ rdb_status rdb_regressor_gram_sharded_host(rdb_chain* const* chains, int32_t n_c
  *                         bytes to every rank out of band; the group then has ONE local device.
  * The group owns one chain handle per local device (rdb_group_chain: same chain, usable with every other entry point on that device).
  * rdb_regressor_gram_sharded: shards[k], tau_meas[k] (array or its entries may be NULL), gram[k] / rhs[k] / tau_sq[k] (entries may be NULL:
- * that device does not receive the result) are DEVICE pointers on local device k; streams[k] (array or entries may be NULL = the group's own
- * stream of that device; wait with rdb_group_synchronize).  Every non-NULL output receives the sum over ALL ranks (added to its contents when
+ * that device does not receive the result) are DEVICE pointers on local device k; streams[k] is the cudaStream_t of device k (an entry of 0 is
+ * the default stream, as everywhere in CUDA); streams == NULL runs every device on the group's own stream (wait with rdb_group_synchronize).  Every non-NULL output receives the sum over ALL ranks (added to its contents when
  * accumulate != 0).  Asynchronous.  NCCL's summation order is fixed for a given number of ranks but differs from the single-GPU order:
  * compare with a tolerance, not bit for bit. */
 typedef struct rdb_group rdb_group; /* opaque */

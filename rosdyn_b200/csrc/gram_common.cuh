@@ -236,7 +236,9 @@ __device__ __forceinline__ void st_row(double* p, double v)
   else *p = v;
 }
 
-template <int NJ, bool REV, int X, int Z = 0, bool GLOBAL = false>
+// LAZY: Dq / DDq of a link are loaded inside the walk (the compiler hoists them as far as registers allow) instead of being held in registers
+// from before the wait for the output buffer: with two generator warps per sub-partition the latency hides behind the other warp
+template <int NJ, bool REV, int X, int Z = 0, bool GLOBAL = false, bool LAZY = false>
 __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramComps* comps, const GenIn<NJ>& x, const SamplesDev& in,
                                               const double* __restrict__ tau_meas, double* __restrict__ slot, int64_t i, int lane)
 {
@@ -252,7 +254,7 @@ __device__ __forceinline__ void gram_generate(const ChainDev<NJ>& C, const GramC
   for (int l = 0; l < NJ; l++)
   {
     const JointDev& J = C.joint[l];
-    const double dql = x.dq[l], ddql = x.ddq[l];
+    const double dql = LAZY ? ld_in(in.dq, J.in, in.ld, i) : x.dq[l], ddql = LAZY ? ld_in(in.ddq, J.in, in.ld, i) : x.ddq[l];
     double R[9];
     V3 t = v3(J.t);
     if (REV || J.type == RDB_JOINT_REVOLUTE)

@@ -154,10 +154,11 @@ __global__ void __launch_bounds__(32 * (GR_MMA_WARPS + GR_GENS), 1)
     {
       const int64_t i = ((int64_t)blockIdx.x + k * gridDim.x) * 32 + lane;
       GenIn<NJ> cur;
-      gen_load<NJ>(C, in, min(i, in.n - 1), cur);
+#pragma unroll
+      for (int l = 0; l < NJ; l++) cur.q[l] = ld_in(in.q, C.joint[l].in, in.ld, min(i, in.n - 1));
       trig_all<NJ>(cur.q, cur.sv, cur.cv);
       if (m > 0) mbar_wait(&bars.ring_free[e], (m - 1) & 1);  // the previous contents have been copied out
-      gram_generate<NJ, REV, 0, Z, true>(C, nullptr, cur, in, tau_meas, entry, min(i, in.n - 1), lane);
+      gram_generate<NJ, REV, 0, Z, true, true>(C, nullptr, cur, in, tau_meas, entry, min(i, in.n - 1), lane);
       if (i >= in.n) gram_zero_lane<NJ, 0, Z, true>(entry, lane);
       // the rows were written through the generic proxy; the TMA engine reads them through the async proxy
       __threadfence();

@@ -259,7 +259,7 @@ rdb_status rdb_regressor_gram_sharded(rdb_group* g, const rdb_samples* shards, c
   // 1. every local device: fused regressor -> normal equations of its shard, written straight into the packed buffer
   for (int k = 0; k < nd; k++)
   {
-    cudaStream_t st = streams && streams[k] ? (cudaStream_t)streams[k] : g->streams[(size_t)k];
+    cudaStream_t st = streams ? (cudaStream_t)streams[k] : g->streams[(size_t)k];  // an entry of `streams` may be 0 = the default stream
     double* pk = g->packed[(size_t)k];
     const rdb_status s = rdb_regressor_gram_batch(g->chains[(size_t)k], &shards[k], tau_meas ? tau_meas[k] : nullptr, pk, pk + (size_t)P * P,
                                                   pk + (size_t)P * P + P, 0, st);
@@ -272,7 +272,7 @@ rdb_status rdb_regressor_gram_sharded(rdb_group* g, const rdb_samples* shards, c
     if (r != kNcclSuccess) return nccl_fail(r, "ncclGroupStart");
     for (int k = 0; k < nd; k++)
     {
-      cudaStream_t st = streams && streams[k] ? (cudaStream_t)streams[k] : g->streams[(size_t)k];
+      cudaStream_t st = streams ? (cudaStream_t)streams[k] : g->streams[(size_t)k];  // an entry of `streams` may be 0 = the default stream
       DeviceScope dev(rdb_chain_device(g->chains[(size_t)k]));
       r = a.AllReduce(g->packed[(size_t)k], g->packed[(size_t)k], n_out, kNcclDouble, kNcclSum, g->comms[(size_t)k], st);
       if (r != kNcclSuccess) break;
@@ -288,7 +288,7 @@ rdb_status rdb_regressor_gram_sharded(rdb_group* g, const rdb_samples* shards, c
     double* b = rhs ? rhs[k] : nullptr;
     double* t = tau_sq ? tau_sq[k] : nullptr;
     if (!G && !b && !t) continue;
-    cudaStream_t st = streams && streams[k] ? (cudaStream_t)streams[k] : g->streams[(size_t)k];
+    cudaStream_t st = streams ? (cudaStream_t)streams[k] : g->streams[(size_t)k];  // an entry of `streams` may be 0 = the default stream
     DeviceScope dev(rdb_chain_device(g->chains[(size_t)k]));
     group_unpack_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(g->packed[(size_t)k], P, G, b, t, accumulate);
     count_launch();

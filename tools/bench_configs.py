@@ -58,7 +58,7 @@ def cpu_config1(out):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,2,3,4,5,h")
+    ap.add_argument("--configs", default="1,2,3,4,5,h,g")
     ap.add_argument("--min-seconds", type=float, default=1.0)
     ap.add_argument("--scale", type=float, default=1.0, help="multiply every sample count (smoke runs)")
     args = ap.parse_args()
@@ -115,8 +115,10 @@ def main():
             pass_fn()
         sync_all()
         total_ms, passes = 0.0, 0
+        wall0 = time.perf_counter()
         with ClockSampler(local) as clk:
-            while total_ms < args.min_seconds * 1e3 and passes < 10000:
+            # at least min-seconds of timed kernels, but never more than 30 s of wall clock per config (untimed regeneration included)
+            while total_ms < args.min_seconds * 1e3 and passes < 10000 and time.perf_counter() - wall0 < 30.0:
                 if between:
                     between()
                     torch.cuda.synchronize()
@@ -291,6 +293,30 @@ def main():
             sec, passes, clk = timed(pe, total)
             report("headline (materialised, RDB_LAYOUT_EIGEN records): C6, 1e8 samples, getRegressor + torque", total, sec, passes, clk,
                    bytes_per_sample=8 * (18 + 420 + 6), chunks=len(smps))
+    # ------------------------------------------------------------------ chains the unrolled kernels do not cover (> 8 moving joints): *_kernel_generic
+    if "g" in want and world == 1:
+        d = fixtures.random_chain(909, 12, p_prismatic=0.1, p_fixed=0.0)   # 12 moving joints: runtime loops, model in global memory
+        ch = Chain(d)
+        n_in, P, total = d.n_inputs, 10 * d.n_joints, N(2e6)
+        q, dq, ddq = inputs(n_in, total, 9)
+        tau = torch.empty((n_in, total), dtype=torch.float64, device=dev)
+        phi = torch.empty((P * n_in, total), dtype=torch.float64, device=dev)
+        smp = CSamples(total, total, q.data_ptr(), dq.data_ptr(), ddq.data_ptr(), None)
+        sec, passes, clk = timed(lambda: check(lib.rdb_torque_batch(ch._h, ctypes.byref(smp), tau.data_ptr(), total, stream())), total)
+        report("generic kernels: 12 moving joints, getJointTorque [dyn_kernel_generic<TORQUE>]", total, sec, passes, clk, bytes_per_sample=8 * 4 * n_in,
+               note="chains with more than 8 moving joints: runtime loops, per-joint state in local memory")
+        sec, passes, clk = timed(lambda: check(lib.rdb_regressor_batch(ch._h, ctypes.byref(smp), phi.data_ptr(), None, total, stream())), total)
+        report("generic kernels: 12 moving joints, getRegressor 12x120 [dyn_kernel_generic<REGRESSOR>]", total, sec, passes, clk,
+               bytes_per_sample=8 * (3 * n_in + P * n_in))
+        G = torch.empty((P, P), dtype=torch.float64, device=dev)
+        b = torch.empty((P,), dtype=torch.float64, device=dev)
+        tt = torch.empty((1,), dtype=torch.float64, device=dev)
+        sec, passes, clk = timed(lambda: check(lib.rdb_regressor_gram_batch(ch._h, ctypes.byref(smp), None, G.data_ptr(), b.data_ptr(), tt.data_ptr(), 0,
+                                                                            stream())), total)
+        report("general Gram pipeline: 12 moving joints (dyn_kernel_generic -> L2-sized workspace -> syrk_dmma_kernel)", total, sec, passes, clk,
+               flop_per_sample=n_in * P * (P + 1) + 2 * n_in * P)
+        del phi, tau, q, dq, ddq
+        torch.cuda.empty_cache()
     if world > 1:
         dist.destroy_process_group()
 
