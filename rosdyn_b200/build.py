@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OBJDIR = os.path.join(ROOT, "build")
 LIB = os.path.join(HERE, "librosdyn_b200.so")
-SOURCES = ["kernels.cu", "gram.cu", "gram_fused.cu", "gram_ring.cu", "components.cu", "aux.cu", "ik.cu", "group.cu", "capi.cu", "urdf.cpp", "solve.cpp", "fold.cpp"]
+SOURCES = ["kernels.cu", "gram.cu", "gram_fused.cu", "components.cu", "aux.cu", "ik.cu", "group.cu", "capi.cu", "urdf.cpp", "solve.cpp", "fold.cpp"]
 HEADERS = ["chain_dev.h", "spatial.cuh", "launch.h", "gram_common.cuh", os.path.join("..", "..", "include", "rosdyn_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",

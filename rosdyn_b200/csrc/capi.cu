@@ -248,7 +248,6 @@ void rdb_chain_destroy(rdb_chain* chain)
   if (chain->gram.fused_partials) cudaFree(chain->gram.fused_partials);
   if (chain->gram.fold_dev) cudaFree(chain->gram.fold_dev);
   if (chain->gram.ext_dev) cudaFree(chain->gram.ext_dev);
-  if (chain->gram.ring) cudaFree(chain->gram.ring);
   if (chain->host_arena.base) cudaFree(chain->host_arena.base);
   for (int k = 0; k < 2; k++)
     if (chain->host_arena.st[k]) cudaStreamDestroy(chain->host_arena.st[k]);

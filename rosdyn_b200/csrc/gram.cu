@@ -180,19 +180,14 @@ cudaError_t launch_gram(ChainHost& ch, const SamplesDev& in, const double* tau_m
     // library) can force the general pipeline with RDB_GRAM_IMPL=v0
 #ifdef RDB_DEV_SWITCHES
     static const bool force_v0 = [] { const char* e = getenv("RDB_GRAM_IMPL"); return e && e[0] == 'v'; }();
-    static const bool force_slots = [] { const char* e = getenv("RDB_GRAM_IMPL"); return e && e[0] == 's'; }();  // A/B: gram_fused.cu
 #else
-    constexpr bool force_v0 = false, force_slots = false;
+    constexpr bool force_v0 = false;
 #endif
     if (!force_v0)
     {
       cudaError_t e = cudaErrorNotSupported;
       if (P == Pr)
-      {
-        // rigid-body model: the ring kernel (gram_ring.cu) first, the slot kernel (gram_fused.cu) when the chain does not fit it
-        if (!force_slots) e = launch_gram_ring(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
-        if (e == cudaErrorNotSupported) e = launch_gram_fused(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
-      }
+        e = launch_gram_fused(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
       else
         e = launch_gram_fused_ext(ch, in, tau_meas, gram, rhs, tau_sq, accumulate, st);
       if (e != cudaErrorNotSupported) return e;

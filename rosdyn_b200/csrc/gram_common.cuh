@@ -15,6 +15,9 @@ namespace rdb
 #ifndef GF_TSPLIT
 #define GF_TSPLIT 2
 #endif
+#ifndef GF_ZCOL
+#define GF_ZCOL 1  // all-revolute chains: drop the exact-zero mass column of a link on its own joint (GramGeom Z)
+#endif
 constexpr int GF_KSPLIT = 4;      // MMA warps that share the k-steps of a slot (one per SM sub-partition)
 constexpr int GF_TS = GF_TSPLIT;  // 1: each MMA warp owns all tiles; 2: two warps per sub-partition split the tile rows by parity
 constexpr int GF_MMA_WARPS = GF_KSPLIT * GF_TS;

@@ -37,10 +37,10 @@ namespace rdb
 
 // ---------------------------------------------------------------------------------------------- MMA side
 // B fragments of one k-step (4 samples of joint row J, k-step kk of the slot): lane (g, t) holds column 8 I + g of sample 4 kk + t
-template <int NJ, int J, int X = 0>
-__device__ __forceinline__ void gram_load_frags(const double* __restrict__ slot, int kk, int lane, double (&b)[GramGeom<NJ>::T])
+template <int NJ, int J, int X = 0, int Z = 0>
+__device__ __forceinline__ void gram_load_frags(const double* __restrict__ slot, int kk, int lane, double (&b)[GramGeom<NJ, 0, Z>::T])
 {
-  using G = GramGeom<NJ, X>;
+  using G = GramGeom<NJ, X, Z>;
   constexpr int T = G::T, L = G::rowlen(J), TJ = G::tj(J);
   const int g = lane >> 2, t = lane & 3;
   const double* rowp = slot + G::rowbase(J) + ((4 * kk + t) ^ (4 * (g & 3)));
@@ -53,10 +53,10 @@ __device__ __forceinline__ void gram_load_frags(const double* __restrict__ slot,
     else b[I] = 0.0;
   }
 }
-template <int NJ, int PAR, int J>
-__device__ __forceinline__ void gram_mma_step(const double (&b)[GramGeom<NJ>::T], double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
+template <int NJ, int PAR, int J, int Z>
+__device__ __forceinline__ void gram_mma_step(const double (&b)[GramGeom<NJ, 0, Z>::T], double (&acc)[GramGeom<NJ, 0, Z>::ntiles(GF_TS, PAR)][2])
 {
-  using G = GramGeom<NJ>;
+  using G = GramGeom<NJ, 0, Z>;
   constexpr int T = G::T, TJ = G::tj(J);
 #pragma unroll
   for (int I = 0; I < T; I++)
@@ -69,61 +69,65 @@ __device__ __forceinline__ void gram_mma_step(const double (&b)[GramGeom<NJ>::T]
 }
 // k-steps STEP.. of this warp in one slot; step = (joint row, k-step of the warp); the fragments of the next step are in flight while the
 // DMMAs of the current one issue
-template <int NJ, int PAR, int STEP>
-__device__ __forceinline__ void gram_consume_steps(const double* __restrict__ slot, int ks, int lane, const double (&bcur)[GramGeom<NJ>::T],
-                                                   double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2])
+template <int NJ, int PAR, int STEP, int Z>
+__device__ __forceinline__ void gram_consume_steps(const double* __restrict__ slot, int ks, int lane, const double (&bcur)[GramGeom<NJ, 0, Z>::T],
+                                                   double (&acc)[GramGeom<NJ, 0, Z>::ntiles(GF_TS, PAR)][2])
 {
-  using G = GramGeom<NJ>;
+  using G = GramGeom<NJ, 0, Z>;
   constexpr int J = STEP / G::KPW;
   if constexpr (STEP + 1 < G::NSTEPS)
   {
     double bnext[G::T];
-    gram_load_frags<NJ, (STEP + 1) / G::KPW>(slot, ks * G::KPW + (STEP + 1) % G::KPW, lane, bnext);
-    gram_mma_step<NJ, PAR, J>(bcur, acc);
-    gram_consume_steps<NJ, PAR, STEP + 1>(slot, ks, lane, bnext, acc);
+    gram_load_frags<NJ, (STEP + 1) / G::KPW, 0, Z>(slot, ks * G::KPW + (STEP + 1) % G::KPW, lane, bnext);
+    gram_mma_step<NJ, PAR, J, Z>(bcur, acc);
+    gram_consume_steps<NJ, PAR, STEP + 1, Z>(slot, ks, lane, bnext, acc);
   }
   else
-    gram_mma_step<NJ, PAR, J>(bcur, acc);
+    gram_mma_step<NJ, PAR, J, Z>(bcur, acc);
+}
+// the k-steps of one slot for this warp
+template <int NJ, int PAR, int Z>
+__device__ __forceinline__ void gram_consume_slot(const double* __restrict__ slot, int ks, int lane,
+                                                  double (&acc)[GramGeom<NJ, 0, Z>::ntiles(GF_TS, PAR)][2])
+{
+  using G = GramGeom<NJ, 0, Z>;
+  double b0[G::T];
+  gram_load_frags<NJ, 0, 0, Z>(slot, ks * G::KPW, lane, b0);
+  gram_consume_steps<NJ, PAR, 0, Z>(slot, ks, lane, b0, acc);
 }
 
 struct GramBars
 {
   uint64_t full[GF_MAX_SLOTS], empty[GF_MAX_SLOTS];
+  // GENS != SLOTS (more generator warps than slots, e.g. 4 over the 3 slots of a 7-joint chain): the writer of a slot changes from use to use,
+  // so a waiter can be more than one phase behind and the one-bit phase parity of an mbarrier is ambiguous; monotone counters instead
+  uint32_t filled[GF_MAX_SLOTS];   // uses of the slot written so far (generator, release)
+  uint32_t drained[GF_MAX_SLOTS];  // MMA-warp completions on the slot so far (GF_MMA_WARPS per use, release)
 };
-
-template <int NJ, int SLOTS, int PAR>
-__device__ __forceinline__ void gram_mma_role(const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane, int dbg)
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
 {
-  using G = GramGeom<NJ>;
-  constexpr int NTP = G::ntiles(GF_TS, PAR);
-  double acc[NTP][2];
-#pragma unroll
-  for (int k = 0; k < NTP; k++) acc[k][0] = acc[k][1] = 0.0;
-  const int64_t ngroups = (in.n + 31) / 32;
-  const int64_t stride = (int64_t)gridDim.x * SLOTS;
-  uint32_t parity = 0;
-  for (int64_t base = (int64_t)blockIdx.x * SLOTS; base < ngroups; base += stride, parity ^= 1)
-  {
-#pragma unroll 1
-    for (int s = 0; s < SLOTS; s++)
-    {
-      if (base + s >= ngroups) break;
-      const double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
-      mbar_wait(&bars->full[s], parity);
-      if (!(dbg & 2))
-      {
-        double b0[G::T];
-        gram_load_frags<NJ, 0>(slot, ks * G::KPW, lane, b0);
-        gram_consume_steps<NJ, PAR, 0>(slot, ks, lane, b0, acc);
-      }
-      if (base + s + stride < ngroups)  // the generator will come back for this slot
-      {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->empty[s]);
-      }
-    }
-  }
-  // fixed-order reduction over the k-split warps that own the same tiles, into shared memory (the slots are dead by now)
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_inc(uint32_t* p)
+{
+  asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+}
+__device__ __forceinline__ void wait_counter_ge(const uint32_t* p, uint32_t v)
+{
+  while (ld_acquire_u32(p) < v) __nanosleep(32);
+}
+
+// fixed-order reduction over the k-split warps that own the same tiles, into shared memory (the slots are dead by now)
+template <int NJ, int PAR, int Z>
+__device__ __forceinline__ void gram_mma_reduce(double (&acc)[GramGeom<NJ, 0, Z>::ntiles(GF_TS, PAR)][2], double* smem, int ks, int lane)
+{
+  using G = GramGeom<NJ, 0, Z>;
   bar_sync(GF_BAR_REDUCE, 32 * GF_MMA_WARPS);
   const int g = lane >> 2, t = lane & 3;
   for (int w = 0; w < GF_KSPLIT; w++)
@@ -154,6 +158,39 @@ __device__ __forceinline__ void gram_mma_role(const SamplesDev& in, double* smem
     }
     bar_sync(GF_BAR_REDUCE, 32 * GF_MMA_WARPS);
   }
+}
+
+template <int NJ, int SLOTS, int PAR, int Z>
+__device__ __forceinline__ void gram_mma_role(const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane, int dbg)
+{
+  using G = GramGeom<NJ, 0, Z>;
+  constexpr int NTP = G::ntiles(GF_TS, PAR);
+  double acc[NTP][2];
+#pragma unroll
+  for (int k = 0; k < NTP; k++) acc[k][0] = acc[k][1] = 0.0;
+  const int64_t ngroups = (in.n + 31) / 32;
+  const int64_t stride = (int64_t)gridDim.x * SLOTS;
+  uint32_t parity = 0;
+  for (int64_t base = (int64_t)blockIdx.x * SLOTS; base < ngroups; base += stride, parity ^= 1)
+  {
+#pragma unroll 1
+    for (int s = 0; s < SLOTS; s++)
+    {
+      if (base + s >= ngroups) break;
+      const double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
+      mbar_wait(&bars->full[s], parity);
+      if (!(dbg & 2))
+      {
+        gram_consume_slot<NJ, PAR, Z>(slot, ks, lane, acc);
+      }
+      if (base + s + stride < ngroups)  // the generator will come back for this slot
+      {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->empty[s]);
+      }
+    }
+  }
+  gram_mma_reduce<NJ, PAR, Z>(acc, smem, ks, lane);
 }
 
 // ---------------------------------------------------------------------------------------------- MMA side, cross mode
@@ -267,11 +304,11 @@ __device__ __forceinline__ void gram_cross_role(const SamplesDev& in, double* sm
   }
 }
 
-template <int NJ, int SLOTS, bool REV, int X>
+template <int NJ, int SLOTS, bool REV, int X, int Z>
 __device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const GramComps& comps, const SamplesDev& in,
                                               const double* __restrict__ tau_meas, double* smem, GramBars* bars, int s, int lane, int dbg)
 {
-  using G = GramGeom<NJ, X>;
+  using G = GramGeom<NJ, X, Z>;
   double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
   const int64_t ngroups = (in.n + 31) / 32;
   const int64_t stride = (int64_t)gridDim.x * SLOTS;
@@ -286,20 +323,82 @@ __device__ __forceinline__ void gram_gen_role(const ChainDev<NJ>& C, const GramC
     mbar_wait(&bars->empty[s], parity);  // consumers released the slot
     if (!(dbg & 1))
     {
-      gram_generate<NJ, REV, X>(C, &comps, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
-      if (i >= in.n) gram_zero_lane<NJ, X>(slot, lane);
+      gram_generate<NJ, REV, X, Z>(C, &comps, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
+      if (i >= in.n) gram_zero_lane<NJ, X, Z>(slot, lane);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars->full[s]);
   }
 }
 
-template <int NJ, int SLOTS, bool REV, int X>
-__global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
+// ---------------------------------------------------------------------------------------------- GENS generator warps over SLOTS slots
+// The k-th group of a CTA (global group blockIdx.x + k gridDim.x) is produced by generator warp k % GENS into slot k % SLOTS (its use k / SLOTS)
+// and consumed in order by the MMA warps.  With more generator warps than slots every SM sub-partition hosts a generator (7-joint chains have
+// 3 slots: with one generator per slot the fourth sub-partition's FP64 datapath idled whenever the MMA warps waited) and a generator starts
+// the walk of its next group while the previous ones are still being consumed.
+template <int NJ, int SLOTS, int GENS, bool REV, int Z>
+__device__ __forceinline__ void gram_gen_role_c(const ChainDev<NJ>& C, const SamplesDev& in, const double* __restrict__ tau_meas, double* smem,
+                                                GramBars* bars, int w, int lane, int dbg)
+{
+  using G = GramGeom<NJ, 0, Z>;
+  const int64_t ngroups = (in.n + 31) / 32;
+  const int64_t nk = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  for (int64_t k = w; k < nk; k += GENS)
+  {
+    const int s = (int)(k % SLOTS);
+    const uint32_t u = (uint32_t)(k / SLOTS);
+    const int64_t i = ((int64_t)blockIdx.x + k * gridDim.x) * 32 + lane;
+    GenIn<NJ> cur;
+    gen_load<NJ>(C, in, min(i, in.n - 1), cur);
+    trig_all<NJ>(cur.q, cur.sv, cur.cv);
+    wait_counter_ge(&bars->drained[s], GF_MMA_WARPS * u);  // every MMA warp is done with the previous use of the slot
+    double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
+    if (!(dbg & 1))
+    {
+      gram_generate<NJ, REV, 0, Z>(C, nullptr, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
+      if (i >= in.n) gram_zero_lane<NJ, 0, Z>(slot, lane);
+    }
+    __syncwarp();
+    if (lane == 0) st_release_u32(&bars->filled[s], u + 1);
+  }
+}
+
+template <int NJ, int SLOTS, int PAR, int Z>
+__device__ __forceinline__ void gram_mma_role_c(const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane, int dbg)
+{
+  using G = GramGeom<NJ, 0, Z>;
+  constexpr int NTP = G::ntiles(GF_TS, PAR);
+  double acc[NTP][2];
+#pragma unroll
+  for (int k = 0; k < NTP; k++) acc[k][0] = acc[k][1] = 0.0;
+  const int64_t ngroups = (in.n + 31) / 32;
+  const int64_t nk = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+#pragma unroll 1
+  for (int64_t k = 0; k < nk; k++)
+  {
+    const int s = (int)(k % SLOTS);
+    const uint32_t u = (uint32_t)(k / SLOTS);
+    const double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
+    wait_counter_ge(&bars->filled[s], u + 1);
+    if (!(dbg & 2))
+    {
+      gram_consume_slot<NJ, PAR, Z>(slot, ks, lane, acc);
+    }
+    __syncwarp();
+    if (lane == 0) red_release_inc(&bars->drained[s]);
+  }
+  gram_mma_reduce<NJ, PAR, Z>(acc, smem, ks, lane);
+}
+
+template <int NJ, int SLOTS, bool REV, int X, int GENS = SLOTS>
+__global__ void __launch_bounds__(GramGeom<NJ>::threads(GENS), 1)
     gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const __grid_constant__ GramComps comps, const SamplesDev in,
                       const double* __restrict__ tau_meas, double* __restrict__ partial, const int dbg)
 {
-  using G = GramGeom<NJ, X>;
+  // Z (gram_common.cuh): on all-revolute chains the mass column of a link on its own joint is an exact zero; it is put last in its block and
+  // neither stored nor multiplied (rigid-body mode only: 98 instead of 104 DMMA per 4 samples for 6 joints, 143 instead of 149 for 7)
+  constexpr int Z = GF_ZCOL && REV && X == 0 ? 1 : 0;
+  using G = GramGeom<NJ, X, Z>;
   extern __shared__ __align__(16) double smem[];
   __shared__ GramBars bars;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -309,6 +408,8 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
     {
       mbar_init(&bars.full[s], 1);              // lane 0 of the generator warp, after __syncwarp
       mbar_init(&bars.empty[s], GF_MMA_WARPS);  // lane 0 of every MMA warp
+      bars.filled[s] = 0;
+      bars.drained[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -316,7 +417,8 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
   // group of (iteration it, CTA, slot s): (it*gridDim.x + blockIdx.x)*SLOTS + s ; generator warp s fills slot s
   if (warp >= GF_MMA_WARPS)
   {
-    gram_gen_role<NJ, SLOTS, REV, X>(C, comps, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
+    if constexpr (GENS != SLOTS) gram_gen_role_c<NJ, SLOTS, GENS, REV, Z>(C, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
+    else gram_gen_role<NJ, SLOTS, REV, X, Z>(C, comps, in, tau_meas, smem, &bars, warp - GF_MMA_WARPS, lane, dbg);
     return;
   }
   // ------------------------------------------------ MMA warps: k-split index = warp % 4 (its SM sub-partition), tile-row parity = warp / 4
@@ -330,16 +432,26 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(SLOTS), 1)
   }
   else
   {
-    if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, SLOTS, 0>(in, smem, &bars, ks, lane, dbg);
-    else gram_mma_role<NJ, SLOTS, 1>(in, smem, &bars, ks, lane, dbg);
+    if constexpr (GENS != SLOTS)
+    {
+      if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role_c<NJ, SLOTS, 0, Z>(in, smem, &bars, ks, lane, dbg);
+      else gram_mma_role_c<NJ, SLOTS, 1, Z>(in, smem, &bars, ks, lane, dbg);
+    }
+    else
+    {
+      if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_mma_role<NJ, SLOTS, 0, Z>(in, smem, &bars, ks, lane, dbg);
+      else gram_mma_role<NJ, SLOTS, 1, Z>(in, smem, &bars, ks, lane, dbg);
+    }
   }
   double* out = partial + (size_t)blockIdx.x * NOUT;
   for (int k = mma_id * 32 + lane; k < NOUT; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
 }
 
 // fixed-order sum of the per-CTA partials -> gram (full symmetric, column-major), rhs, tau_sq
+// zcol: GramGeom Z = 1 position order (the mass column last in every link block; position P does not exist and the row / column of the first
+// moving link's mass, an identically zero column of Phi, is written as exact zeros)
 __global__ void gram_fused_reduce_kernel(const double* __restrict__ partial, int nparts, int T, int P, double* __restrict__ gram,
-                                         double* __restrict__ rhs, double* __restrict__ tau_sq, int accumulate)
+                                         double* __restrict__ rhs, double* __restrict__ tau_sq, int accumulate, int zcol)
 {
   const int NT = T * (T + 1) / 2;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,12 +466,25 @@ __global__ void gram_fused_reduce_kernel(const double* __restrict__ partial, int
   }
   const int J = I + k;
   const int rp = 8 * I + ((e >> 3) & 7), cp = 8 * J + (e & 7);  // positions inside the kernel (GramGeom::pos)
-  if (rp > P || cp > P) return;
+  if (zcol && e <= P && !accumulate)  // the untouched mass column of the first moving link (parameter 0): exact zeros
+  {
+    if (e == P) rhs[0] = 0.0;
+    else
+    {
+      gram[(size_t)e * P] = 0.0;
+      gram[e] = 0.0;
+    }
+  }
+  if (rp > P - zcol || cp > P - zcol) return;
   if (I == J && rp > cp) return;  // diagonal tiles hold both halves; keep the upper one
   // position -> column of the (folded) parameter vector, P = tau
   const int nj = P / 10;
-  const int row = rp == 0 ? P : 10 * (nj - 1 - (rp - 1) / 10) + (rp - 1) % 10;
-  const int col = cp == 0 ? P : 10 * (nj - 1 - (cp - 1) / 10) + (cp - 1) % 10;
+  auto col_of = [&](int pos) {
+    if (pos == 0) return P;
+    const int q = (pos - 1) % 10;
+    return 10 * (nj - 1 - (pos - 1) / 10) + (zcol ? (q == 9 ? 0 : q + 1) : q);
+  };
+  const int row = col_of(rp), col = col_of(cp);
   if (row < P && col < P)
   {
     const double v = accumulate ? gram[(size_t)col * P + row] + s : s;
@@ -461,29 +586,41 @@ static cudaError_t grow(double*& p, size_t& have, size_t need)
   return e;
 }
 
+// generator warps of the rigid-body kernel: one per SM sub-partition even when fewer slots fit (GF_GENS4 = 0: one per slot, as before)
+#ifndef GF_GENS4
+#define GF_GENS4 1
+#endif
+template <int SLOTS>
+constexpr int gf_gens()
+{
+  return (GF_GENS4 && GF_TS == 2 && SLOTS < 4) ? 4 : SLOTS;
+}
+
 template <int NJ, int SLOTS, bool REV>
 static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
                                    int accumulate, cudaStream_t st)
 {
-  using G = GramGeom<NJ>;
+  constexpr int GENS = gf_gens<SLOTS>();
+  constexpr int Z = GF_ZCOL && REV ? 1 : 0;  // as in the kernel
+  using G = GramGeom<NJ, 0, Z>;
   const size_t smem = sizeof(double) * (size_t)std::max(G::SLOT_DOUBLES * SLOTS, G::NT * 64);
   {
-    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS, REV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS, REV, 0, GENS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   const int dbg = gram_dev_switch();
   const int64_t ngroups = (in.n + 31) / 32;
-  const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + SLOTS - 1) / SLOTS);
+  const int grid = (int)std::min<int64_t>(ch.sm_count, GENS != SLOTS ? ngroups : (ngroups + SLOTS - 1) / SLOTS);
   {
     cudaError_t e = grow(ch.gram.fused_partials, ch.gram.fused_bytes, sizeof(double) * (size_t)ch.sm_count * G::NT * 64);
     if (e != cudaSuccess) return e;
   }
-  gram_fused_kernel<NJ, SLOTS, REV, 0><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), GramComps{}, in, tau_meas,
-                                                                              ch.gram.fused_partials, dbg);
+  gram_fused_kernel<NJ, SLOTS, REV, 0, GENS><<<grid, G::threads(GENS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), GramComps{}, in, tau_meas,
+                                                                                   ch.gram.fused_partials, dbg);
   count_launch();
   if (ch.gram.fold_identity)
   {
-    gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, gram, rhs, tau_sq, accumulate);
+    gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, gram, rhs, tau_sq, accumulate, Z);
     count_launch();
     return cudaGetLastError();
   }
@@ -493,7 +630,7 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const do
   double* Gr = Tm + (size_t)nj * 100;
   double* br = Gr + (size_t)Pr * Pr;
   double* tsr = br + Pr;
-  gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, Gr, br, tsr, 0);
+  gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, Gr, br, tsr, 0, Z);
   count_launch();
   return launch_fold_expand(ch, gram, rhs, tau_sq, accumulate, st);
 }

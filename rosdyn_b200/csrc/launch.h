@@ -25,8 +25,6 @@ struct GramWorkspace
   size_t fold_bytes = 0;
   double* ext_dev = nullptr;   // extended model: rigid-body block | cross-tile sums | cross partials | component map
   size_t ext_bytes = 0;
-  double* ring = nullptr;      // gram_ring.cu: L2-resident ring between the generator warps and the shared-memory slots (per CTA, per generator)
-  size_t ring_bytes = 0;
 };
 
 // persistent pipeline of rdb_regressor_gram_batch_host (capi.cu)
@@ -138,9 +136,6 @@ cudaError_t fold_chain(ChainHost& ch);
 // gram_fused.cu: cudaErrorNotSupported when the chain does not fit the fused kernel
 cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
                               int accumulate, cudaStream_t st);
-// gram_ring.cu: the same normal equations with the generator warps decoupled from the slots through an L2-resident ring (TMA bulk copies)
-cudaError_t launch_gram_ring(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
-                             int accumulate, cudaStream_t st);
 // gram_fused.cu: G = E^T G' E, b = E^T b' from the reduced (folded-chain) normal equations kept in ch.gram.fold_dev
 cudaError_t launch_fold_expand(ChainHost& ch, double* gram, double* rhs, double* tau_sq, int accumulate, cudaStream_t st);
 // same for the extended model [Phi | Phi_c] (gram is Pt x Pt, Pt = 10 nJ + component columns)

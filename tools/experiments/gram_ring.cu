@@ -33,6 +33,7 @@ namespace rdb
 constexpr int GR_GENS = 8;       // generator warps per CTA = ring entries per CTA
 constexpr int GR_MMA_WARPS = 4;  // one per SM sub-partition (k-split), each owns all tiles
 constexpr int GR_BAR_REDUCE = 1;
+constexpr int GR_BAR_PAIR0 = 2;    // named barriers 2..5: the two generator warps of a sub-partition
 
 struct RingBars
 {
@@ -147,21 +148,43 @@ __global__ void __launch_bounds__(32 * (GR_MMA_WARPS + GR_GENS), 1)
   if (warp >= GR_MMA_WARPS)
   {
     // ------------------------------------------------ generator warp e: groups e, e + GR_GENS, ...
-    const int e = warp - GR_MMA_WARPS;
+    // The two generator warps of sub-partition s (warps 4 + s and 8 + s) produce adjacent groups (ring entries 2 s and 2 s + 1) and enter the
+    // walk of every group together (named barrier 2 + s): they then go through the ~65 KB of unrolled generator code side by side and share its
+    // instruction-cache lines.  Eight warps at eight unrelated places of that code miss the instruction cache on 40 % of their issue slots
+    // (profiles/r02_gram_ring_v1_ncu.txt: no_instruction 6.1 stalls per issue).
+    const int sp = (warp - GR_MMA_WARPS) & 3, half = (warp - GR_MMA_WARPS) >> 2;
+    const int e = 2 * sp + half;
     double* const entry = my_ring + (size_t)e * G::SLOT_DOUBLES;
-    uint32_t m = 0;  // uses of the entry so far
-    for (int64_t k = e; k < nk; k += GR_GENS, m++)
+    const int64_t pair_iters = nk > 2 * sp ? (nk - 2 * sp + GR_GENS - 1) / GR_GENS : 0;  // iterations of the pair's first warp (>= the second's)
+    for (int64_t m64 = 0; m64 < pair_iters; m64++)
     {
+      const uint32_t m = (uint32_t)m64;  // uses of the entry so far
+      const int64_t k = e + m64 * GR_GENS;
+      const bool work = k < nk;
       const int64_t i = ((int64_t)blockIdx.x + k * gridDim.x) * 32 + lane;
       GenIn<NJ> cur;
+#ifdef RING_EAGER_LOADS
+      gen_load<NJ>(C, in, min(i, in.n - 1), cur);
+#else
 #pragma unroll
       for (int l = 0; l < NJ; l++) cur.q[l] = ld_in(in.q, C.joint[l].in, in.ld, min(i, in.n - 1));
+#endif
       trig_all<NJ>(cur.q, cur.sv, cur.cv);
-      if (m > 0) mbar_wait(&bars.ring_free[e], (m - 1) & 1);  // the previous contents have been copied out
+      if (work && m > 0) mbar_wait(&bars.ring_free[e], (m - 1) & 1);  // the previous contents have been copied out
+#ifndef RING_UNPAIRED
+      bar_sync(GR_BAR_PAIR0 + sp, 64);
+#endif
+      if (!work) continue;
+#ifdef RING_EAGER_LOADS
+      gram_generate<NJ, REV, 0, Z, true, false>(C, nullptr, cur, in, tau_meas, entry, min(i, in.n - 1), lane);
+#else
       gram_generate<NJ, REV, 0, Z, true, true>(C, nullptr, cur, in, tau_meas, entry, min(i, in.n - 1), lane);
+#endif
       if (i >= in.n) gram_zero_lane<NJ, 0, Z, true>(entry, lane);
       // the rows were written through the generic proxy; the TMA engine reads them through the async proxy
+#ifndef RING_NO_THREADFENCE
       __threadfence();
+#endif
       asm volatile("fence.proxy.async;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.ring_full[e]);
