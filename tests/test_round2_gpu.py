@@ -302,3 +302,16 @@ def test_gram_is_bit_reproducible(name, torch):
         for _ in range(4):
             G, b, tt = ch.regressorGram(q, dq, ddq)
             assert torch.equal(G, G0) and torch.equal(b, b0) and torch.equal(tt, t0)
+
+
+def test_cpp_group_example(torch):
+    """examples/group_check.cpp: rdb_group_create / rdb_regressor_gram_sharded from plain C++ on every GPU of the box (one GPU: no collective,
+    same path) against the host-sum entry."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "build", "group_check")
+    if not os.path.exists(exe):
+        pytest.skip("build/group_check not built")
+    r = subprocess.run([exe, str(torch.cuda.device_count()), "400003"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "group_check: ok" in r.stdout, r.stdout + r.stderr
