@@ -162,6 +162,8 @@ struct GramComps
   int32_t ncols[8];
   int32_t kind[8][GX_COLS];
   double thr[8][GX_COLS], vmax[8][GX_COLS];
+  double ithr[8][GX_COLS];  // 1 / thr (the normal equations multiply by it: a double division costs ~35 FP64 instructions; the materialised
+                            // component regressor of components.cu keeps the reference's division)
 };
 
 // ---------------------------------------------------------------------------------------------- generator
@@ -188,20 +190,26 @@ __device__ __forceinline__ void gen_load(const ChainDev<NJ>& C, const SamplesDev
 // [0; axis] at birth) loses its linear terms.
 // Component columns of every joint row (element-wise in q_j, Dq_j; zero padded to one tile), written after the walk by ONE rolled loop over
 // (joint, column): no call (a called function costs the walker its registers through the ABI -- it spilled 280 bytes per thread into an L1
-// that the slots leave at ~20 KB), little code, and the walk stays one basic block.  q_j / Dq_j are read again (L2 hits).
+// that the slots leave at ~20 KB), little code, and the walk stays one basic block.
 template <int NJ>
 __device__ __forceinline__ void gram_component_columns(const ChainDev<NJ>& C, const GramComps& comps, const SamplesDev& in, int64_t i,
                                                        double* __restrict__ slot, int lane)
 {
   using G = GramGeom<NJ, 1>;
-  int base = 0;
-#pragma unroll 1
+  // q_j / Dq_j are read again (L2 hits; keeping them in registers through the walk spills), ALL joints at once so that the loads overlap;
+  // joint loop unrolled, column loop rolled: little code, no call
+  double qv[NJ], dqv[NJ];
+#pragma unroll
   for (int j = 0; j < NJ; j++)
   {
-    const int len = 1 + 10 * (NJ - j);  // rowlen(j): regular positions of row j; the component columns follow
-    const int jin = C.joint[j].in, nc = comps.ncols[j];
-    const double q = ld_in(in.q, jin, in.ld, i), dq = ld_in(in.dq, jin, in.ld, i);
-    double* o = slot + base + len * 32;
+    qv[j] = ld_in(in.q, C.joint[j].in, in.ld, i);
+    dqv[j] = ld_in(in.dq, C.joint[j].in, in.ld, i);
+  }
+  static_for<0, NJ>([&](auto jc) {
+    constexpr int j = decltype(jc)::value;
+    const double q = qv[j], dq = dqv[j];
+    const int nc = comps.ncols[j];
+    double* o = slot + G::rowbase(j) + G::rowlen(j) * 32;
 #pragma unroll 1
     for (int c = 0; c < GX_COLS; c++)
     {
@@ -216,7 +224,7 @@ __device__ __forceinline__ void gram_component_columns(const ChainDev<NJ>& C, co
         else if (kd == GXK_ONE) val = 1.0;
         else
         {
-          const double r = omega / th;
+          const double r = omega * comps.ithr[j][c];
           if (kd == GXK_SAT) val = fmin(fmax(r, -1.0), 1.0);
           else
           {
@@ -227,8 +235,7 @@ __device__ __forceinline__ void gram_component_columns(const ChainDev<NJ>& C, co
       }
       o[c * 32 + (lane ^ (4 * (c & 3)))] = val;
     }
-    base += (len + GX_COLS) * 32;
-  }
+  });
 }
 
 // GLOBAL: the rows go to an L2-resident ring entry in global memory (st.global.cg: no L1 allocation) instead of a shared-memory slot

@@ -14,15 +14,24 @@
 //     sub-partitions split the k-steps of a slot, GF_TSPLIT warps per sub-partition split the tile rows by parity.  The k-steps of a slot
 //     are fully unrolled and software pipelined: the fragments of step n+1 are loaded while the DMMAs of step n issue.
 //     tcgen05 has no f64 kind: the FP64 tensor path of sm_100a is mma.sync.m8n8k4.f64 (SASS DMMA).
-//   * slots cycle through shared-memory mbarriers (full / empty per slot); as many slots as fit the 227 KB (3 for 7 joints, 4 below).
+//   * slots cycle through shared-memory mbarriers (full / empty per slot); as many slots as fit the 227 KB (3 for 7 joints, 4 below).  Chains
+//     with only 3 slots still run 4 generator warps, one per SM sub-partition, over them (monotone counters instead of the one-bit mbarrier
+//     phase: the writer of a slot changes from use to use).
+//   * all-revolute chains drop the exact-zero mass column of a link on its own joint (GramGeom Z): the rows are one position shorter,
+//     98 instead of 104 DMMA per 4 samples for 6 joints (143 / 149 for 7).
 // Per-CTA partials are summed in a fixed order by gram_fused_reduce_kernel (bit-reproducible for a given n).
+// gram_ext_kernel: the extended model [Phi | Phi_c] (friction / spring columns) in ONE pass -- the rows carry the component columns of their
+// joint, the MMA warps keep the rigid-body tiles and the cross tiles in registers.
 //
-// What bounds it (ncu, profiles/r01_gram_fused_v3_ncu.txt): DMMA and DFMA share ONE FP64 datapath; a DMMA occupies it for 16 cycles, a DFMA
-// for 2 (tools/micro/dfma_latency.cu), and the warp scheduler grants it per instruction, so while the MMA warps work on a slot the generators
-// crawl and the two phases effectively alternate; the generator alone is latency bound (one warp per 32 samples).  Measured slower and
-// removed: splitting the rows of a slot over several generator warps (each group its own unrolled code: instruction-cache misses), two lanes
-// per sample with 14 warps (the 16 K registers of a sub-partition cap 4 warps at 128 registers: the walker spills), per-row slot release,
-// an uneven k-split between the sub-partitions.
+// What bounds it (round 2: profiles/r02_micro_datapath_sharing.txt, tools/micro/dfma_halfwarp.cu): DMMA and DFMA share ONE FP64 datapath per
+// sub-partition; a DMMA holds it for 16 cycles, a DFMA for 2.  With the two MMA warps of a sub-partition active the generator warp there gets
+// NOTHING (measured: DMMA 99 %, DFMA 0.1 % of the datapath; with one DMMA warp the DFMA warp gets 15 %), so generation happens in the gaps
+// where the MMA warps wait, and a lone generator warp keeps the datapath ~45 % busy (a third of its instructions are not FP64).  Generation
+// alone takes 4.9 ms per 16 M samples, the MMAs alone 6.3 ms, together 9.2 ms (C6).  More generator warps need more samples in flight than
+// the shared memory holds; decoupling them through an L2-resident ring was built and measured slower (tools/experiments/README.md).
+// Measured slower / no gain and removed: one MMA warp per sub-partition with 254 registers (1.72 vs 1.75 G samples/s), fragments two k-steps
+// ahead (no change), row groups split over several generator warps (instruction-cache misses), two lanes per sample, per-row slot release, an
+// uneven k-split between the sub-partitions.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -96,6 +105,9 @@ __device__ __forceinline__ void gram_consume_slot(const double* __restrict__ slo
   gram_consume_steps<NJ, PAR, 0, Z>(slot, ks, lane, b0, acc);
 }
 
+#ifndef GF_SPIN_NS
+#define GF_SPIN_NS 32  // back-off of the counter polls
+#endif
 struct GramBars
 {
   uint64_t full[GF_MAX_SLOTS], empty[GF_MAX_SLOTS];
@@ -120,7 +132,7 @@ __device__ __forceinline__ void red_release_inc(uint32_t* p)
 }
 __device__ __forceinline__ void wait_counter_ge(const uint32_t* p, uint32_t v)
 {
-  while (ld_acquire_u32(p) < v) __nanosleep(32);
+  while (ld_acquire_u32(p) < v) __nanosleep(GF_SPIN_NS);
 }
 
 // fixed-order reduction over the k-split warps that own the same tiles, into shared memory (the slots are dead by now)
@@ -219,59 +231,11 @@ __device__ __forceinline__ void gram_cross_step(const double (&b)[GramGeom<NJ>::
     }
   });
 }
-template <int NJ, int PAR, int STEP>
-__device__ __forceinline__ void gram_cross_steps(const double* __restrict__ slot, int ks, int lane, const double (&bcur)[GramGeom<NJ>::T], double bxcur,
-                                                 double (&acc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2])
+// fixed-order reduction of the cross tiles over the k-split warps into shared memory at `smem` (NXT tiles of 64 doubles)
+template <int NJ, int PAR>
+__device__ __forceinline__ void gram_cross_reduce_smem(double (&acc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2], double* smem, int ks, int lane)
 {
   using G = GramGeom<NJ, 1>;
-  constexpr int J = STEP / G::KPW;
-  if constexpr (STEP + 1 < G::NSTEPS)
-  {
-    double bnext[G::T];
-    constexpr int JN = (STEP + 1) / G::KPW;
-    const int kn = ks * G::KPW + (STEP + 1) % G::KPW;
-    gram_load_frags<NJ, JN, 1>(slot, kn, lane, bnext);
-    const double bxn = gram_load_xfrag<NJ, JN>(slot, kn, lane);
-    gram_cross_step<NJ, PAR, J>(bcur, bxcur, acc);
-    gram_cross_steps<NJ, PAR, STEP + 1>(slot, ks, lane, bnext, bxn, acc);
-  }
-  else
-    gram_cross_step<NJ, PAR, J>(bcur, bxcur, acc);
-}
-
-template <int NJ, int SLOTS, int PAR>
-__device__ __forceinline__ void gram_cross_role(const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane, int dbg)
-{
-  using G = GramGeom<NJ, 1>;
-  constexpr int NXP = G::nxtiles(GF_TS, PAR);
-  double acc[NXP][2];
-#pragma unroll
-  for (int k = 0; k < NXP; k++) acc[k][0] = acc[k][1] = 0.0;
-  const int64_t ngroups = (in.n + 31) / 32;
-  const int64_t stride = (int64_t)gridDim.x * SLOTS;
-  uint32_t parity = 0;
-  for (int64_t base = (int64_t)blockIdx.x * SLOTS; base < ngroups; base += stride, parity ^= 1)
-  {
-#pragma unroll 1
-    for (int s = 0; s < SLOTS; s++)
-    {
-      if (base + s >= ngroups) break;
-      const double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
-      mbar_wait(&bars->full[s], parity);
-      if (!(dbg & 2))
-      {
-        double b0[G::T];
-        gram_load_frags<NJ, 0, 1>(slot, ks * G::KPW, lane, b0);
-        const double bx0 = gram_load_xfrag<NJ, 0>(slot, ks * G::KPW, lane);
-        gram_cross_steps<NJ, PAR, 0>(slot, ks, lane, b0, bx0, acc);
-      }
-      if (base + s + stride < ngroups)
-      {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->empty[s]);
-      }
-    }
-  }
   bar_sync(GF_BAR_REDUCE, 32 * GF_MMA_WARPS);
   const int g = lane >> 2, t = lane & 3;
   for (int w = 0; w < GF_KSPLIT; w++)
@@ -390,6 +354,110 @@ __device__ __forceinline__ void gram_mma_role_c(const SamplesDev& in, double* sm
   gram_mma_reduce<NJ, PAR, Z>(acc, smem, ks, lane);
 }
 
+// ---------------------------------------------------------------------------------------------- extended model [Phi | Phi_c] in ONE pass
+// The rows carry the component columns of their joint (X = 1 slot geometry); the MMA warps keep BOTH tile sets in registers -- the upper
+// triangular rigid-body tiles and, per joint row, the (regular tile, component tile) / (component, component) cross tiles -- so Phi is
+// generated once (the two-pass scheme walked every chain twice: rigid-body kernel + cross mode).  Counter handshake, GENS generator warps.
+template <int NJ, int PAR, int STEP>
+__device__ __forceinline__ void gram_ext_steps(const double* __restrict__ slot, int ks, int lane, const double (&bcur)[GramGeom<NJ>::T], double bxcur,
+                                               double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2],
+                                               double (&xacc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2])
+{
+  using G = GramGeom<NJ, 1>;
+  constexpr int J = STEP / G::KPW;
+  if constexpr (STEP + 1 < G::NSTEPS)
+  {
+    double bnext[G::T];
+    constexpr int JN = (STEP + 1) / G::KPW;
+    const int kn = ks * G::KPW + (STEP + 1) % G::KPW;
+    gram_load_frags<NJ, JN, 1>(slot, kn, lane, bnext);
+    const double bxn = gram_load_xfrag<NJ, JN>(slot, kn, lane);
+    gram_mma_step<NJ, PAR, J, 0>(bcur, acc);
+    gram_cross_step<NJ, PAR, J>(bcur, bxcur, xacc);
+    gram_ext_steps<NJ, PAR, STEP + 1>(slot, ks, lane, bnext, bxn, acc, xacc);
+  }
+  else
+  {
+    gram_mma_step<NJ, PAR, J, 0>(bcur, acc);
+    gram_cross_step<NJ, PAR, J>(bcur, bxcur, xacc);
+  }
+}
+
+template <int NJ, int SLOTS, int PAR>
+__device__ __forceinline__ void gram_ext_mma_role(const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane)
+{
+  using G = GramGeom<NJ, 1>;
+  using G0 = GramGeom<NJ>;
+  double acc[G0::ntiles(GF_TS, PAR)][2], xacc[G::nxtiles(GF_TS, PAR)][2];
+#pragma unroll
+  for (int k = 0; k < G0::ntiles(GF_TS, PAR); k++) acc[k][0] = acc[k][1] = 0.0;
+#pragma unroll
+  for (int k = 0; k < G::nxtiles(GF_TS, PAR); k++) xacc[k][0] = xacc[k][1] = 0.0;
+  const int64_t ngroups = (in.n + 31) / 32;
+  const int64_t nk = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+#pragma unroll 1
+  for (int64_t k = 0; k < nk; k++)
+  {
+    const int s = (int)(k % SLOTS);
+    const uint32_t u = (uint32_t)(k / SLOTS);
+    const double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
+    wait_counter_ge(&bars->filled[s], u + 1);
+    double b0[G::T];
+    gram_load_frags<NJ, 0, 1>(slot, ks * G::KPW, lane, b0);
+    const double bx0 = gram_load_xfrag<NJ, 0>(slot, ks * G::KPW, lane);
+    gram_ext_steps<NJ, PAR, 0>(slot, ks, lane, b0, bx0, acc, xacc);
+    __syncwarp();
+    if (lane == 0) red_release_inc(&bars->drained[s]);
+  }
+  gram_mma_reduce<NJ, PAR, 0>(acc, smem, ks, lane);                        // rigid-body tiles: smem[0, NT * 64)
+  gram_cross_reduce_smem<NJ, PAR>(xacc, smem + G0::NT * 64, ks, lane);    // cross tiles behind them
+}
+
+template <int NJ, int SLOTS, int GENS, bool REV>
+__global__ void __launch_bounds__(GramGeom<NJ>::threads(GENS), 1)
+    gram_ext_kernel(const __grid_constant__ ChainDev<NJ> C, const __grid_constant__ GramComps comps, const SamplesDev in,
+                    const double* __restrict__ tau_meas, double* __restrict__ partial)
+{
+  using G = GramGeom<NJ, 1>;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ GramBars bars;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < SLOTS)
+  {
+    bars.filled[threadIdx.x] = 0;
+    bars.drained[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  if (warp >= GF_MMA_WARPS)
+  {
+    const int w = warp - GF_MMA_WARPS;
+    const int64_t ngroups = (in.n + 31) / 32;
+    const int64_t nk = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    for (int64_t k = w; k < nk; k += GENS)
+    {
+      const int s = (int)(k % SLOTS);
+      const uint32_t u = (uint32_t)(k / SLOTS);
+      const int64_t i = ((int64_t)blockIdx.x + k * gridDim.x) * 32 + lane;
+      GenIn<NJ> cur;
+      gen_load<NJ>(C, in, min(i, in.n - 1), cur);
+      trig_all<NJ>(cur.q, cur.sv, cur.cv);
+      wait_counter_ge(&bars.drained[s], GF_MMA_WARPS * u);
+      double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
+      gram_generate<NJ, REV, 1>(C, &comps, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
+      if (i >= in.n) gram_zero_lane<NJ, 1>(slot, lane);
+      __syncwarp();
+      if (lane == 0) st_release_u32(&bars.filled[s], u + 1);
+    }
+    return;
+  }
+  const int mma_id = warp, ks = mma_id % GF_KSPLIT;
+  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_ext_mma_role<NJ, SLOTS, 0>(in, smem, &bars, ks, lane);
+  else gram_ext_mma_role<NJ, SLOTS, 1>(in, smem, &bars, ks, lane);
+  constexpr int NOUT = (GramGeom<NJ>::NT + G::NXT) * 64;
+  double* out = partial + (size_t)blockIdx.x * NOUT;
+  for (int k = mma_id * 32 + lane; k < NOUT; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
+}
+
 template <int NJ, int SLOTS, bool REV, int X, int GENS = SLOTS>
 __global__ void __launch_bounds__(GramGeom<NJ>::threads(GENS), 1)
     gram_fused_kernel(const __grid_constant__ ChainDev<NJ> C, const __grid_constant__ GramComps comps, const SamplesDev in,
@@ -425,12 +493,7 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(GENS), 1)
   const int mma_id = warp;
   const int ks = mma_id % GF_KSPLIT;
   constexpr int NOUT = (X ? G::NXT : G::NT) * 64;
-  if (X)
-  {
-    if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_cross_role<NJ, SLOTS, 0>(in, smem, &bars, ks, lane, dbg);
-    else gram_cross_role<NJ, SLOTS, 1>(in, smem, &bars, ks, lane, dbg);
-  }
-  else
+  static_assert(X == 0, "the extended model runs through gram_ext_kernel");
   {
     if constexpr (GENS != SLOTS)
     {
@@ -451,13 +514,13 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(GENS), 1)
 // zcol: GramGeom Z = 1 position order (the mass column last in every link block; position P does not exist and the row / column of the first
 // moving link's mass, an identically zero column of Phi, is written as exact zeros)
 __global__ void gram_fused_reduce_kernel(const double* __restrict__ partial, int nparts, int T, int P, double* __restrict__ gram,
-                                         double* __restrict__ rhs, double* __restrict__ tau_sq, int accumulate, int zcol)
+                                         double* __restrict__ rhs, double* __restrict__ tau_sq, int accumulate, int zcol, int pstride)
 {
   const int NT = T * (T + 1) / 2;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= NT * 64) return;
   double s = 0.0;
-  for (int p = 0; p < nparts; p++) s += partial[(size_t)p * NT * 64 + e];
+  for (int p = 0; p < nparts; p++) s += partial[(size_t)p * pstride + e];  // pstride: doubles between the partials of two CTAs
   int k = e >> 6, I = 0;
   while (k >= T - I)
   {
@@ -620,7 +683,7 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const do
   count_launch();
   if (ch.gram.fold_identity)
   {
-    gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, gram, rhs, tau_sq, accumulate, Z);
+    gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, gram, rhs, tau_sq, accumulate, Z, G::NT * 64);
     count_launch();
     return cudaGetLastError();
   }
@@ -630,7 +693,7 @@ static cudaError_t launch_fused_nj(ChainHost& ch, const SamplesDev& in, const do
   double* Gr = Tm + (size_t)nj * 100;
   double* br = Gr + (size_t)Pr * Pr;
   double* tsr = br + Pr;
-  gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, Gr, br, tsr, 0, Z);
+  gram_fused_reduce_kernel<<<(G::NT * 64 + 255) / 256, 256, 0, st>>>(ch.gram.fused_partials, grid, G::T, G::P, Gr, br, tsr, 0, Z, G::NT * 64);
   count_launch();
   return launch_fold_expand(ch, gram, rhs, tau_sq, accumulate, st);
 }
@@ -663,12 +726,12 @@ cudaError_t launch_gram_fused(ChainHost& ch, const SamplesDev& in, const double*
 
 // ---------------------------------------------------------------------------------------------- extended model [Phi | Phi_c]
 // sum of the per-CTA cross partials in a fixed order
-__global__ void gram_cross_reduce_kernel(const double* __restrict__ partial, int nparts, int n, double* __restrict__ sum)
+__global__ void gram_cross_reduce_kernel(const double* __restrict__ partial, int nparts, int n, int pstride, double* __restrict__ sum)
 {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   double s = 0.0;
-  for (int p = 0; p < nparts; p++) s += partial[(size_t)p * n + e];
+  for (int p = 0; p < nparts; p++) s += partial[(size_t)p * pstride + e];
   sum[e] = s;
 }
 
@@ -742,25 +805,46 @@ __global__ void gram_cross_finish_kernel(const double* __restrict__ X, const dou
   }
 }
 
-template <int NJ, int SLOTS, bool REV>
-static cudaError_t launch_cross_nj(ChainHost& ch, const GramComps& gc, const SamplesDev& in, const double* tau_meas, double* xpartial, double* xsum,
-                                   cudaStream_t st)
+// single pass (gram_ext_kernel): rigid-body tiles -> Gt | bt | tst (full parameter vector), cross tiles -> xsum
+template <int NJ, bool REV>
+static cudaError_t launch_ext_nj(ChainHost& ch, const GramComps& gc, const SamplesDev& in, const double* tau_meas, double* Gt, double* bt, double* tst,
+                                 double* xpart, double* xsum, cudaStream_t st)
 {
   using G = GramGeom<NJ, 1>;
-  const size_t smem = sizeof(double) * (size_t)std::max(G::SLOT_DOUBLES * SLOTS, G::NXT * 64);
-  cudaError_t e = cudaFuncSetAttribute(gram_fused_kernel<NJ, SLOTS, REV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  using G0 = GramGeom<NJ>;
+  constexpr int SLOTS = gf_slots<NJ, 1>();
+  constexpr int GENS = GF_TS == 2 ? 4 : SLOTS;  // 8 MMA + 4 generator warps (one per SM sub-partition) whatever the number of slots
+  constexpr int PSTRIDE = (G0::NT + G::NXT) * 64;
+  const size_t smem = sizeof(double) * (size_t)std::max(G::SLOT_DOUBLES * SLOTS, PSTRIDE);
+  cudaError_t e = cudaFuncSetAttribute(gram_ext_kernel<NJ, SLOTS, GENS, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t ngroups = (in.n + 31) / 32;
-  const int grid = (int)std::min<int64_t>(ch.sm_count, (ngroups + SLOTS - 1) / SLOTS);
-  const int dbg = gram_dev_switch();
-  gram_fused_kernel<NJ, SLOTS, REV, 1><<<grid, G::threads(SLOTS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), gc, in, tau_meas, xpartial, dbg);
+  const int grid = (int)std::min<int64_t>(ch.sm_count, ngroups);
+  gram_ext_kernel<NJ, SLOTS, GENS, REV><<<grid, G0::threads(GENS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), gc, in, tau_meas, xpart);
   count_launch();
-  gram_cross_reduce_kernel<<<(G::NXT * 64 + 255) / 256, 256, 0, st>>>(xpartial, grid, G::NXT * 64, xsum);
+  const int nred = (G0::NT * 64 + 255) / 256;
+  if (ch.gram.fold_identity)
+  {
+    gram_fused_reduce_kernel<<<nred, 256, 0, st>>>(xpart, grid, G0::T, G0::P, Gt, bt, tst, 0, 0, PSTRIDE);
+    count_launch();
+  }
+  else
+  {
+    const int nj = ch.host.nj, Pr = G0::P;
+    double* Gr = ch.gram.fold_dev + (size_t)nj * 100;
+    double* br = Gr + (size_t)Pr * Pr;
+    gram_fused_reduce_kernel<<<nred, 256, 0, st>>>(xpart, grid, G0::T, G0::P, Gr, br, br + Pr, 0, 0, PSTRIDE);
+    count_launch();
+    e = launch_fold_expand(ch, Gt, bt, tst, 0, st);
+    if (e != cudaSuccess) return e;
+  }
+  gram_cross_reduce_kernel<<<(G::NXT * 64 + 255) / 256, 256, 0, st>>>(xpart + G0::NT * 64, grid, G::NXT * 64, PSTRIDE, xsum);
   count_launch();
   return cudaGetLastError();
 }
 
-// Normal equations of the extended model: the rigid-body block from the X = 0 kernel, the component blocks from the cross mode.
+// Normal equations of the extended model in one pass over the samples (gram_ext_kernel); the two-pass scheme (rigid-body kernel, then the cross
+// mode of gram_fused_kernel) is kept for development builds (RDB_GRAM_EXT=2).
 // cudaErrorNotSupported: more than 7 moving joints, a component on an input no chain joint feeds, or more than GX_COLS component columns
 // on one joint (caller falls back to the general pipeline).
 cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const double* tau_meas, double* gram, double* rhs, double* tau_sq,
@@ -786,6 +870,7 @@ cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const dou
       const int g = gc.ncols[j]++;
       gc.kind[j][g] = kinds[row][p];
       gc.thr[j][g] = c.thr;
+      gc.ithr[j][g] = 1.0 / c.thr;
       gc.vmax[j][g] = c.vmax;
       xmap[c.col + p] = j;
       xmap[Pc + c.col + p] = g;
@@ -795,8 +880,9 @@ cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const dou
   for (int j = 0; j < K; j++) rev = rev && F.joint[j].type == RDB_JOINT_REVOLUTE;
   int nxt = 0;
   for (int j = 0; j < K; j++) nxt += (1 + 10 * (K - j) + 7) / 8 + 1;  // GramGeom::nxt
-  // workspace: rigid block (P*P + P + 1) | cross sums (nxt*64) | cross partials (sm_count*nxt*64) | component map (2 Pc ints)
-  const size_t n_rigid = (size_t)P * P + P + 1, n_sum = (size_t)nxt * 64, n_part = (size_t)ch.sm_count * nxt * 64;
+  const int Tt = (10 * K + 8) / 8, ntt = Tt * (Tt + 1) / 2;            // GramGeom::T, NT
+  // workspace: rigid block (P*P + P + 1) | cross sums (nxt*64) | per-CTA partials (sm_count*(ntt+nxt)*64) | component map (2 Pc ints)
+  const size_t n_rigid = (size_t)P * P + P + 1, n_sum = (size_t)nxt * 64, n_part = (size_t)ch.sm_count * (ntt + nxt) * 64;
   cudaError_t e = grow(ch.gram.ext_dev, ch.gram.ext_bytes, sizeof(double) * (n_rigid + n_sum + n_part) + sizeof(int32_t) * 2 * (size_t)Pc);
   if (e != cudaSuccess) return e;
   double* Gt = ch.gram.ext_dev;
@@ -807,27 +893,24 @@ cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const dou
   int32_t* dmap = reinterpret_cast<int32_t*>(xpart + n_part);
   e = cudaMemcpyAsync(dmap, xmap.data(), sizeof(int32_t) * xmap.size(), cudaMemcpyHostToDevice, st);  // pageable source: staged before return
   if (e != cudaSuccess) return e;
-  // rigid-body block
-  e = launch_gram_fused(ch, in, tau_meas, Gt, bt, tst, 0, st);
-  if (e != cudaSuccess) return e;
-  gram_ext_scatter_kernel<<<(P * (P + 1) + 255) / 256, 256, 0, st>>>(Gt, bt, tst, P, Pt, gram, rhs, tau_sq, accumulate);
-  count_launch();
-  // component blocks
   switch (K)
   {
-#define X(N)                                                                                     \
-  case N:                                                                                        \
-    e = rev ? launch_cross_nj<N, gf_slots<N, 1>(), true>(ch, gc, in, tau_meas, xpart, xsum, st) \
-            : launch_cross_nj<N, gf_slots<N, 1>(), false>(ch, gc, in, tau_meas, xpart, xsum, st); \
-    break;
+#define X(N)                                                                                    \
+  case N:                                                                                       \
+  e = rev ? launch_ext_nj<N, true>(ch, gc, in, tau_meas, Gt, bt, tst, xpart, xsum, st)        \
+          : launch_ext_nj<N, false>(ch, gc, in, tau_meas, Gt, bt, tst, xpart, xsum, st);      \
+  break;
     X(1) X(2) X(3) X(4) X(5) X(6) X(7)
 #undef X
   }
   if (e != cudaSuccess) return e;
-  const double* Tm = ch.gram.fold_identity ? nullptr : ch.gram.fold_dev;
-  const int32_t* kof = ch.gram.fold_identity ? nullptr
-                                             : reinterpret_cast<const int32_t*>(ch.gram.fold_dev + (size_t)nj * 100 + (size_t)(10 * K + 1) * (10 * K + 1));
-  gram_cross_finish_kernel<<<((P + 1 + Pc) * Pc + 127) / 128, 128, 0, st>>>(xsum, Tm, kof, dmap, dmap + Pc, nj, K, Pc, gram, rhs, accumulate);
+  gram_ext_scatter_kernel<<<(P * (P + 1) + 255) / 256, 256, 0, st>>>(Gt, bt, tst, P, Pt, gram, rhs, tau_sq, accumulate);
+  count_launch();
+  const double* Tm1 = ch.gram.fold_identity ? nullptr : ch.gram.fold_dev;
+  const int32_t* kof1 = ch.gram.fold_identity
+                            ? nullptr
+                            : reinterpret_cast<const int32_t*>(ch.gram.fold_dev + (size_t)nj * 100 + (size_t)(10 * K + 1) * (10 * K + 1));
+  gram_cross_finish_kernel<<<((P + 1 + Pc) * Pc + 127) / 128, 128, 0, st>>>(xsum, Tm1, kof1, dmap, dmap + Pc, nj, K, Pc, gram, rhs, accumulate);
   count_launch();
   return cudaGetLastError();
 }
