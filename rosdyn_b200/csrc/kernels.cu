@@ -56,8 +56,13 @@ enum : int
 // axes at the link-l origin, and the unit twists (U[j],S[j]) of all joints j <= l at the same point/axes.
 // REV (unrolled torque / inertia kernels on the folded chain): every joint is revolute, so the joint type is a compile-time fact -- no type
 // selects and the linear half of the joint screws (an exact zero) is never multiplied
-template <int NJ_T, int MODE, bool REV = false, class ChainT>
-__device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, const DynOutDev& out, int64_t i)
+// REC (regressor modes, RDB_LAYOUT_EIGEN): the 10 n_act values a link contributes to a sample's record (a contiguous piece of the column-major
+// n_act x 10 nJ matrix) are staged in a per-warp shared-memory tile [32 samples][10 n_act + 1] and written out row by row, 32 lanes on
+// consecutive doubles -- full sectors instead of one 8-byte piece of 32 different lines per store instruction (0.21 -> see DESIGN.md).
+// `stage` is the warp's tile, `i_live` the number of samples of this warp that exist (all 32 lanes take part in the cooperative copies).
+template <int NJ_T, int MODE, bool REV = false, bool REC = false, class ChainT>
+__device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, const DynOutDev& out, int64_t i, double* stage = nullptr,
+                                         int i_live = 32)
 {
   // element (plane p, sample i) of an output array: base + p * ld_out + i * ss (SoA planes: ld_out = ld, ss = 1; Eigen records: ld_out = 1)
   double* __restrict__ const phi = out.phi + i * out.ss_phi;
@@ -71,6 +76,13 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
   constexpr bool kTau = (MODE & DYN_TORQUE) != 0;
   constexpr bool kInr = (MODE & DYN_INERTIA) != 0;
   constexpr bool kDyn = kReg || kTau;  // needs velocities / accelerations
+  const int lane_r = threadIdx.x & 31;
+  const int W = 10 * n_in, RS = W + 1;                // REC: doubles of one link block of a record, tile row stride (odd: conflict free)
+  double* const my_row = REC ? stage + lane_r * RS : nullptr;
+  if (REC)
+  {
+    for (int c = 0; c < W; c++) my_row[c] = 0.0;      // rows of inputs that no chain joint feeds stay zero (never written below)
+  }
 
   V3 U[CAP], S[CAP];
   double tau[kTau ? CAP : 1];
@@ -233,18 +245,35 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
         }
         if (r >= 0)
         {
-          double* o = phi + (colbase + r) * ld_out;
-          const int64_t st = (int64_t)n_in * ld_out;
-          __stcs(o, e0);
-          __stcs(o + st, h.x);
-          __stcs(o + 2 * st, h.y);
-          __stcs(o + 3 * st, h.z);
-          __stcs(o + 4 * st, e4);
-          __stcs(o + 5 * st, e5);
-          __stcs(o + 6 * st, e6);
-          __stcs(o + 7 * st, e7);
-          __stcs(o + 8 * st, e8);
-          __stcs(o + 9 * st, e9);
+          if (REC)
+          {
+            double* o = my_row + r;
+            o[0] = e0;
+            o[n_in] = h.x;
+            o[2 * n_in] = h.y;
+            o[3 * n_in] = h.z;
+            o[4 * n_in] = e4;
+            o[5 * n_in] = e5;
+            o[6 * n_in] = e6;
+            o[7 * n_in] = e7;
+            o[8 * n_in] = e8;
+            o[9 * n_in] = e9;
+          }
+          else
+          {
+            double* o = phi + (colbase + r) * ld_out;
+            const int64_t st = (int64_t)n_in * ld_out;
+            __stcs(o, e0);
+            __stcs(o + st, h.x);
+            __stcs(o + 2 * st, h.y);
+            __stcs(o + 3 * st, h.z);
+            __stcs(o + 4 * st, e4);
+            __stcs(o + 5 * st, e5);
+            __stcs(o + 6 * st, e6);
+            __stcs(o + 7 * st, e7);
+            __stcs(o + 8 * st, e8);
+            __stcs(o + 9 * st, e9);
+          }
         }
       }
       // rows of the joints after link l are structural zeros of this column block (exact 0.0)
@@ -254,11 +283,33 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
         const int r = C.joint[j].in;
         if (r >= 0)
         {
-          double* o = phi + (colbase + r) * ld_out;
-          const int64_t st = (int64_t)n_in * ld_out;
+          if (REC)
+          {
 #pragma unroll
-          for (int p = 0; p < 10; p++) __stcs(o + p * st, 0.0);
+            for (int p = 0; p < 10; p++) my_row[p * n_in + r] = 0.0;
+          }
+          else
+          {
+            double* o = phi + (colbase + r) * ld_out;
+            const int64_t st = (int64_t)n_in * ld_out;
+#pragma unroll
+            for (int p = 0; p < 10; p++) __stcs(o + p * st, 0.0);
+          }
         }
+      }
+      if (REC)
+      {
+        // the warp's 32 record pieces of this link leave together: sample s -> out.phi + (i - lane + s) * ss_phi + 10 l n_act + [0, W)
+        __syncwarp();
+        const int64_t i0 = __shfl_sync(0xffffffffu, i, 0);  // lane 0 always holds a live sample: the warp's first
+        double* const base = out.phi + i0 * out.ss_phi + colbase;
+        for (int srow = 0; srow < i_live; srow++)
+        {
+          const double* src = stage + srow * RS;
+          double* dst = base + (int64_t)srow * out.ss_phi;
+          for (int c = lane_r; c < W; c += 32) __stcs(dst + c, src[c]);
+        }
+        __syncwarp();
       }
     }
     else if (kTau)
@@ -307,7 +358,7 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
     for (int j = 0; j < (NJ_T > 0 ? NJ_T : nj); j++)
     {
       const int r = C.joint[j].in;
-      if (r >= 0) st_out(tau_out, r, ld_out, i_tau, tau[j]);
+      if (r >= 0 && (!REC || lane_r < i_live)) st_out(tau_out, r, ld_out, i_tau, tau[j]);
     }
   }
   if (kInr)
@@ -328,10 +379,20 @@ __device__ __forceinline__ void dyn_body(const ChainT& C, const SamplesDev& in, 
   }
 }
 
-template <int NJ, int MODE, bool REV = false>
+template <int NJ, int MODE, bool REV = false, bool REC = false>
 __global__ void __launch_bounds__(RDB_BLOCK, (MODE & DYN_REGRESSOR) ? RDB_REG_MINB : RDB_DYN_MINB) dyn_kernel(const __grid_constant__ ChainDev<NJ> C, const SamplesDev in, const DynOutDev out)
 {
   const int64_t i = (int64_t)blockIdx.x * RDB_BLOCK + threadIdx.x;
+  if (REC)
+  {
+    // every lane of a warp that holds at least one sample takes part in the staged copies; lanes past the end recompute the last sample
+    extern __shared__ double dyn_stage[];
+    const int64_t i0 = i - (threadIdx.x & 31);
+    if (i0 >= in.n) return;
+    const int live = (int)min((int64_t)32, in.n - i0);
+    dyn_body<NJ, MODE, REV, true>(C, in, out, min(i, in.n - 1), dyn_stage + (size_t)(threadIdx.x >> 5) * 32 * (10 * C.n_in + 1), live);
+    return;
+  }
   if (i >= in.n) return;
   dyn_body<NJ, MODE, REV>(C, in, out, i);
 }
@@ -776,6 +837,27 @@ static cudaError_t launch_dyn_mode(const ChainHost& ch, const SamplesDev& in, co
   const ChainDev<RDB_MAX_JOINTS>& H = folded ? ch.gram.fold : ch.host;
   bool rev = folded;  // all-revolute specialisation (torque / inertia on the folded chain only)
   for (int j = 0; j < H.nj && rev; j++) rev = H.joint[j].type == RDB_JOINT_REVOLUTE;
+  // regressor in the Eigen-record layout: staged stores (dyn_body REC); the tile is 32 x (10 n_act + 1) doubles per warp
+  if ((MODE & DYN_REGRESSOR) != 0 && out.ps == 1 && out.ss_phi > 1 && H.nj <= 8)
+  {
+    const size_t smem = sizeof(double) * (RDB_BLOCK / 32) * 32 * (size_t)(10 * H.n_in + 1);
+    switch (H.nj)
+    {
+#define X(N)                                                                                                                            \
+  case N:                                                                                                                               \
+  {                                                                                                                                     \
+    auto kern = dyn_kernel<N, (MODE & DYN_REGRESSOR) ? MODE : DYN_REGRESSOR, false, true>;                                              \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                 \
+    if (e != cudaSuccess) return e;                                                                                                     \
+    kern<<<grid, RDB_BLOCK, smem, st>>>(narrow<N>(H), in, out);                                                                         \
+    break;                                                                                                                              \
+  }
+      RDB_FAST_NJ(X)
+#undef X
+    }
+    count_launch();
+    return cudaGetLastError();
+  }
   switch (H.nj)
   {
 #define X(N)                                                                                                                    \
