@@ -306,15 +306,16 @@ def main():
     lib = load()
     n_in, P = d.n_inputs, 10 * d.n_joints
     gram = args.workload == "gram"
-    # Samples per GPU per step.  gram: 64 M samples = 9.2 GB of device-resident inputs, ~35 ms per step, so the driver's 20 steps give a timed
-    # region of >= 0.7 s under sustained clocks / power (8 M samples per step, round 1, timed 0.1 s of burst clocks).  materialise: a step is
-    # `launches` back-to-back launches of 4 M samples each over DISTINCT inputs; Phi (13.6 GB per launch) is overwritten in place.
+    # Samples per GPU per step.  gram: 128 M samples = 18.4 GB of device-resident inputs, ~73 ms per step, so the driver's 20 steps give a
+    # timed region of ~1.5 s under sustained clocks / power (round 1 timed 8 M samples per step: 0.1 s of burst clocks).  materialise: a step
+    # is `launches` back-to-back launches of 4 M samples each over DISTINCT inputs (128 M samples per step: ~75 ms); Phi (13.6 GB per launch)
+    # is overwritten in place.
     if gram:
-        S, launches = (args.samples or 64_000_000), 1
+        S, launches = (args.samples or 128_000_000), 1
         Sl = S
     else:
         Sl = 4_000_000
-        launches = max(1, (args.samples or 32_000_000) // Sl)
+        launches = max(1, (args.samples or 128_000_000) // Sl)
         S = Sl * launches
     # weak scaling: every rank owns its own shard of S samples (disjoint sample indices via the seed offset)
     q, dq, ddq = (fill_uniform(n_in, S, SEED + 1000003 * rank, s, device=dev) for s in range(3))
@@ -464,7 +465,7 @@ def main():
                 "traffic": (tps * Sl) if tps else None,
                 "peak_source": "own FP64 micro-benchmark on this GPU (max of DMMA m8n8k4 and DFMA); MEASURED_PEAKS.json has no FP64 figure",
                 "fp64_peaks_tflops": peaks64, "flop_per_sample": flop, "executed": ex,
-                "kernel": f"gram_fused_kernel<{K},slots> on the folded chain (regressor generation + DMMA normal equations)"}
+                "kernel": (sc.get("kernel") or f"gram_fused_kernel<{K},...>") + " on the folded chain (regressor generation + DMMA normal equations)"}
     else:
         bytes_per_sample = 8 * (3 * n_in + P * n_in + n_in)          # 3552 B for C6
         ach = Sl * bytes_per_sample / per_launch_s / 1e9
