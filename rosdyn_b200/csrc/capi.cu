@@ -249,6 +249,7 @@ void rdb_chain_destroy(rdb_chain* chain)
   if (chain->gram.fold_dev) cudaFree(chain->gram.fold_dev);
   if (chain->gram.ext_dev) cudaFree(chain->gram.ext_dev);
   if (chain->host_arena.base) cudaFree(chain->host_arena.base);
+  if (chain->host_arena.map_h) cudaFreeHost(chain->host_arena.map_h);
   for (int k = 0; k < 2; k++)
     if (chain->host_arena.st[k]) cudaStreamDestroy(chain->host_arena.st[k]);
   GramHostPipe& hp = chain->gram_host;
@@ -629,6 +630,7 @@ struct Plane
   int64_t ld = 0;  // host plane stride
   bool records = false;  // RDB_LAYOUT_EIGEN output: [sample][planes] dense records on both sides (one contiguous copy per chunk)
   double* d[2] = {nullptr, nullptr};
+  double* hm = nullptr;  // mapped mode: host alias of d[0]
 };
 
 struct HostPipe
@@ -636,6 +638,13 @@ struct HostPipe
   cudaStream_t st[2] = {nullptr, nullptr};
   std::vector<Plane*> all;
   int64_t chunk = 0;
+  bool mapped = false;  // the whole call fits the handle's mapped pinned buffer: no copy calls, the kernels work on host memory
+  struct Pending
+  {
+    Plane* p;
+    int64_t off, len;
+  };
+  std::vector<Pending> pending;  // mapped mode: outputs to hand to the caller after the synchronisation
   // device buffers and streams come from the handle's arena (grown on demand, freed with the handle); one host call at a time per handle
   rdb_status init(HostArena& ar, int64_t n, int64_t chunk_max, std::vector<Plane*> planes)
   {
@@ -650,6 +659,24 @@ struct HostPipe
     size_t need = 0;
     for (Plane* p : all)
       if ((p->h_in || p->h_out) && p->planes > 0) need += sizeof(double) * (size_t)p->planes * chunk * slots;
+    if (slots == 1 && need <= RDB_HOST_MAPPED_BYTES)
+    {
+      if (!ar.map_h)
+      {
+        RDB_CUDA(cudaHostAlloc(&ar.map_h, RDB_HOST_MAPPED_BYTES, cudaHostAllocMapped));
+        RDB_CUDA(cudaHostGetDevicePointer(&ar.map_d, ar.map_h, 0));
+      }
+      mapped = true;
+      size_t o = 0;
+      for (Plane* p : all)
+        if ((p->h_in || p->h_out) && p->planes > 0)
+        {
+          p->d[0] = ar.map_d + o;
+          p->hm = ar.map_h + o;
+          o += (size_t)p->planes * chunk;
+        }
+      return RDB_OK;
+    }
     if (ar.bytes < need)
     {
       if (ar.base) cudaFree(ar.base);
@@ -671,6 +698,11 @@ struct HostPipe
   rdb_status h2d(Plane& p, int slot, int64_t off, int64_t len)
   {
     if (!p.h_in || p.planes == 0) return RDB_OK;
+    if (mapped)
+    {
+      for (int64_t r = 0; r < p.planes; r++) memcpy(p.hm + r * chunk, p.h_in + r * p.ld + off, sizeof(double) * (size_t)len);
+      return RDB_OK;
+    }
     RDB_CUDA(cudaMemcpy2DAsync(p.d[slot], chunk * sizeof(double), p.h_in + off, p.ld * sizeof(double), len * sizeof(double), p.planes,
                                cudaMemcpyHostToDevice, st[slot]));
     return RDB_OK;
@@ -678,6 +710,11 @@ struct HostPipe
   rdb_status d2h(Plane& p, int slot, int64_t off, int64_t len)
   {
     if (!p.h_out || p.planes == 0) return RDB_OK;
+    if (mapped)
+    {
+      pending.push_back({&p, off, len});
+      return RDB_OK;
+    }
     if (p.records)
       RDB_CUDA(cudaMemcpyAsync(p.h_out + off * p.planes, p.d[slot], sizeof(double) * (size_t)len * p.planes, cudaMemcpyDeviceToHost, st[slot]));
     else
@@ -688,7 +725,15 @@ struct HostPipe
   rdb_status finish()
   {
     for (int k = 0; k < 2; k++)
-      if (st[k]) RDB_CUDA(cudaStreamSynchronize(st[k]));
+      if (st[k] && (k == 0 || !mapped)) RDB_CUDA(cudaStreamSynchronize(st[k]));
+    for (const Pending& q : pending)
+    {
+      const Plane& p = *q.p;
+      if (p.records) memcpy(p.h_out + q.off * p.planes, p.hm, sizeof(double) * (size_t)q.len * p.planes);
+      else
+        for (int64_t r = 0; r < p.planes; r++) memcpy(p.h_out + r * p.ld + q.off, p.hm + r * chunk, sizeof(double) * (size_t)q.len);
+    }
+    pending.clear();
     return RDB_OK;
   }
 };

@@ -62,7 +62,12 @@ struct HostArena
   double* base = nullptr;
   size_t bytes = 0;
   cudaStream_t st[2] = {nullptr, nullptr};
+  // small calls (a handful of samples, the per-sample getters of the C++ facade): one mapped pinned buffer that the kernels read and write
+  // in place over PCIe -- one launch and one synchronisation instead of a copy call per array
+  double* map_h = nullptr;
+  double* map_d = nullptr;
 };
+constexpr size_t RDB_HOST_MAPPED_BYTES = 256 << 10;
 
 struct ChainHost
 {

@@ -315,3 +315,32 @@ def test_cpp_group_example(torch):
         pytest.skip("build/group_check not built")
     r = subprocess.run([exe, str(torch.cuda.device_count()), "400003"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "group_check: ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("n", [1, 7, 64])
+@pytest.mark.parametrize("layout", ["soa", "eigen"])
+def test_small_host_calls_use_the_same_kernels(n, layout, torch):
+    """Host-buffer calls small enough for the handle's mapped pinned buffer (the per-sample getters of the C++ facade) run the kernels in place on
+    host memory; their results are bit-identical to the device entries on the same samples, and a large call afterwards is unaffected."""
+    from oracle.oracle import fill_uniform
+    from rosdyn_b200.chain import Chain
+    d = fixtures.by_name("c6_perturbed")
+    ch = Chain(d)
+    hq, hdq, hddq, hdddq = (fill_uniform(d.n_inputs, n, 0x5EED0000 + 707, s) for s in range(4))
+    dev = [torch.tensor(x, device="cuda") for x in (hq, hdq, hddq, hdddq)]
+    want = ("T_tool", "T_links", "jacobian", "twist", "dtwist", "ddtwist", "torque")
+    for _ in range(2):  # the second pass reuses the mapped buffer
+        Kh = ch.kinematics(hq, hdq, hddq, hdddq, want=want, layout=layout)
+        Kd = ch.kinematics(*dev, want=want, layout=layout)
+        for k in want:
+            assert isinstance(Kh[k], np.ndarray)
+            assert np.array_equal(Kh[k], _np(Kd[k])), k
+        Dh = ch.dynamics(hq, hdq, hddq, want=("regressor", "torque", "inertia"), layout=layout)
+        Dd = ch.dynamics(*dev[:3], want=("regressor", "torque", "inertia"), layout=layout)
+        for k in ("regressor", "torque", "inertia"):
+            assert np.array_equal(Dh[k], _np(Dd[k])), k
+    assert np.array_equal(ch.getJointTorque(hq, hdq, hddq), _np(ch.getJointTorque(*dev[:3])))
+    big = 300_000
+    bq, bdq, bddq = (fill_uniform(d.n_inputs, big, 0x5EED0000 + 708, s) for s in range(3))
+    tb = ch.getJointTorque(bq, bdq, bddq)
+    assert np.array_equal(tb[:, :1000], _np(ch.getJointTorque(*(torch.tensor(x[:, :1000].copy(), device="cuda") for x in (bq, bdq, bddq)))))
