@@ -31,13 +31,14 @@ __global__ void dfma_lanes(double* out, int iters, int active, long long* cyc)
 
 // warps [0, n_mma) issue DMMAs, warps [n_mma, n_mma + n_dfma) issue DFMAs (ILP 8); all on sub-partition (warp % 4); each role reports the
 // work it completed in a fixed time window (clock64 deadline), i.e. its share of the datapath
-__global__ void share(double* out, long long window, int n_mma, unsigned long long* done)
+__global__ void share(double* out, long long window, int n_mma, unsigned long long* done, int n_dfma_first = 0)
 {
+  // n_dfma_first > 0: the DFMA warps take the LOWEST warp ids instead (does the scheduler's choice depend on the warp id?)
   const int warp = threadIdx.x >> 5;
   double acc = 0;
   unsigned long long n = 0;
   const long long t0 = clock64();
-  if (warp < n_mma)
+  if (n_dfma_first > 0 ? warp >= n_dfma_first : warp < n_mma)
   {
     double d[8][2];
 #pragma unroll
@@ -108,6 +109,18 @@ int main()
       for (int w = 0; w < n_mma + n_dfma; w += 4) (w < n_mma ? m : f) += h[w];
       printf("sub-partition 0 with %d DMMA warp(s) + %d DFMA warp(s): DMMA %.1f%% of the datapath (16 cyc each), DFMA %.1f%% (2 cyc each)\n", n_mma_per,
              n_dfma_per, 100.0 * m * 16 / window, 100.0 * f * 2 / window);
+    }
+  for (int n_mma_per : {1, 2})
+    for (int n_dfma_per : {1, 2})
+    {
+      const int n_mma = 4 * n_mma_per, n_dfma = 4 * n_dfma_per;
+      unsigned long long h[64];
+      share<<<1, 32 * (n_mma + n_dfma)>>>(out, window, n_mma, done, n_dfma);
+      cudaMemcpy(h, done, 8 * (n_mma + n_dfma), cudaMemcpyDeviceToHost);
+      unsigned long long m = 0, f = 0;
+      for (int w = 0; w < n_mma + n_dfma; w += 4) (w >= n_dfma ? m : f) += h[w];
+      printf("DFMA warps FIRST: sub-partition 0 with %d DMMA warp(s) + %d DFMA warp(s): DMMA %.1f%% of the datapath, DFMA %.1f%%\n", n_mma_per, n_dfma_per,
+             100.0 * m * 16 / window, 100.0 * f * 2 / window);
     }
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
