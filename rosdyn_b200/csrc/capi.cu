@@ -661,21 +661,31 @@ struct HostPipe
       if ((p->h_in || p->h_out) && p->planes > 0) need += sizeof(double) * (size_t)p->planes * chunk * slots;
     if (slots == 1 && need <= RDB_HOST_MAPPED_BYTES)
     {
-      if (!ar.map_h)
+      if (!ar.map_h && !ar.map_failed)
       {
-        RDB_CUDA(cudaHostAlloc(&ar.map_h, RDB_HOST_MAPPED_BYTES, cudaHostAllocMapped));
-        RDB_CUDA(cudaHostGetDevicePointer(&ar.map_d, ar.map_h, 0));
-      }
-      mapped = true;
-      size_t o = 0;
-      for (Plane* p : all)
-        if ((p->h_in || p->h_out) && p->planes > 0)
+        // no mapped pinned memory on this host (locked-memory limit, ...): remembered, the copy path below serves small calls as well
+        if (cudaHostAlloc(&ar.map_h, RDB_HOST_MAPPED_BYTES, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&ar.map_d, ar.map_h, 0) != cudaSuccess)
         {
-          p->d[0] = ar.map_d + o;
-          p->hm = ar.map_h + o;
-          o += (size_t)p->planes * chunk;
+          cudaGetLastError();
+          if (ar.map_h) cudaFreeHost(ar.map_h);
+          ar.map_h = ar.map_d = nullptr;
+          ar.map_failed = true;
         }
-      return RDB_OK;
+      }
+      if (ar.map_h)
+      {
+        mapped = true;
+        size_t o = 0;
+        for (Plane* p : all)
+          if ((p->h_in || p->h_out) && p->planes > 0)
+          {
+            p->d[0] = ar.map_d + o;
+            p->hm = ar.map_h + o;
+            o += (size_t)p->planes * chunk;
+          }
+        return RDB_OK;
+      }
     }
     if (ar.bytes < need)
     {

@@ -66,6 +66,7 @@ struct HostArena
   // in place over PCIe -- one launch and one synchronisation instead of a copy call per array
   double* map_h = nullptr;
   double* map_d = nullptr;
+  bool map_failed = false;
 };
 constexpr size_t RDB_HOST_MAPPED_BYTES = 256 << 10;
 
