@@ -217,10 +217,11 @@ __device__ __forceinline__ double gram_load_xfrag(const double* __restrict__ slo
   const int g = lane >> 2, t = lane & 3;
   return slot[G::rowbase(J) + (G::rowlen(J) + g) * 32 + ((4 * kk + t) ^ (4 * (g & 3)))];
 }
-template <int NJ, int PAR, int J>
-__device__ __forceinline__ void gram_cross_step(const double (&b)[GramGeom<NJ>::T], double bx, double (&acc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2])
+template <int NJ, int PAR, int J, int Z = 0>
+__device__ __forceinline__ void gram_cross_step(const double (&b)[GramGeom<NJ, 0, Z>::T], double bx,
+                                                double (&acc)[GramGeom<NJ, 1, Z>::nxtiles(GF_TS, PAR)][2])
 {
-  using G = GramGeom<NJ, 1>;
+  using G = GramGeom<NJ, 1, Z>;
   static_for<0, G::tj(J) + 1>([&](auto Ic) {
     constexpr int I = decltype(Ic)::value;
     if constexpr (G::xowns(J, I, GF_TS, PAR))
@@ -232,10 +233,10 @@ __device__ __forceinline__ void gram_cross_step(const double (&b)[GramGeom<NJ>::
   });
 }
 // fixed-order reduction of the cross tiles over the k-split warps into shared memory at `smem` (NXT tiles of 64 doubles)
-template <int NJ, int PAR>
-__device__ __forceinline__ void gram_cross_reduce_smem(double (&acc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2], double* smem, int ks, int lane)
+template <int NJ, int PAR, int Z = 0>
+__device__ __forceinline__ void gram_cross_reduce_smem(double (&acc)[GramGeom<NJ, 1, Z>::nxtiles(GF_TS, PAR)][2], double* smem, int ks, int lane)
 {
-  using G = GramGeom<NJ, 1>;
+  using G = GramGeom<NJ, 1, Z>;
   bar_sync(GF_BAR_REDUCE, 32 * GF_MMA_WARPS);
   const int g = lane >> 2, t = lane & 3;
   for (int w = 0; w < GF_KSPLIT; w++)
@@ -355,44 +356,108 @@ __device__ __forceinline__ void gram_mma_role_c(const SamplesDev& in, double* sm
 }
 
 // ---------------------------------------------------------------------------------------------- extended model [Phi | Phi_c] in ONE pass
-// The rows carry the component columns of their joint (X = 1 slot geometry); the MMA warps keep BOTH tile sets in registers -- the upper
-// triangular rigid-body tiles and, per joint row, the (regular tile, component tile) / (component, component) cross tiles -- so Phi is
-// generated once (the two-pass scheme walked every chain twice: rigid-body kernel + cross mode).  Counter handshake, GENS generator warps.
-template <int NJ, int PAR, int STEP>
-__device__ __forceinline__ void gram_ext_steps(const double* __restrict__ slot, int ks, int lane, const double (&bcur)[GramGeom<NJ>::T], double bxcur,
-                                               double (&acc)[GramGeom<NJ>::ntiles(GF_TS, PAR)][2],
-                                               double (&xacc)[GramGeom<NJ, 1>::nxtiles(GF_TS, PAR)][2])
+// The slots carry the rigid-body rows in the geometry of the rigid-body kernel (Z: zero mass column dropped on all-revolute chains).  The
+// component columns of a joint -- element-wise functions of that joint's q, Dq (friction_polynomial1.h:45-52, friction_polynomial2.h:42-58,
+// ideal_spring.h:64-70), non-zero in the row of that joint only -- go to a small side buffer next to the slots, XC columns per joint (2, 4
+// or 8: the widest component set of the chain rounded up) instead of a zero-padded 8-column tile inside every row: for 6 joints with a
+// friction model on each the kernel keeps 4 slots (4 x (52.5 + 3) KB) where the padded rows left room for 3 x 66 KB.  The MMA warps keep BOTH
+// tile sets in registers -- the upper triangular rigid-body tiles and, per joint row, the (regular tile, component tile) / (component,
+// component) cross tiles -- so Phi is generated once.  Counter handshake, GENS generator warps.
+template <int NJ, int XC>
+__host__ __device__ constexpr int gram_ext_side_doubles()
 {
-  using G = GramGeom<NJ, 1>;
+  return NJ * XC * 32;
+}
+// component columns of all joints for the lane's sample.  q_j, Dq_j are parked in the buffer itself (columns 1 and 0 of joint j; XC >= 2), then
+// ONE rolled loop over (joint, column) evaluates in place: ~100 instructions instead of 600 for six unrolled joints -- generator plus MMA
+// code of this kernel sit at the size where the instruction caches stop covering both (ncu: no_instruction 24 % of the generator's stalls
+// with the unrolled version)
+template <int NJ, int XC>
+__device__ __forceinline__ void gram_component_side(const GramComps& comps, const GenIn<NJ>& x, double* __restrict__ side, int lane)
+{
+  static_assert(XC >= 2, "q and Dq of a joint are staged in its first two columns");
+#pragma unroll
+  for (int j = 0; j < NJ; j++)
+  {
+    side[(j * XC) * 32 + lane] = x.dq[j];
+    side[(j * XC + 1) * 32 + lane] = x.q[j];
+  }
+#pragma unroll 1
+  for (int j = 0; j < NJ; j++)
+  {
+    double* o = side + (j * XC) * 32 + lane;
+    const double dq = o[0], q = o[32];
+    const int nc = comps.ncols[j];
+#pragma unroll 1
+    for (int c = 0; c < XC; c++)
+    {
+      double val = 0.0;
+      if (c < nc)
+      {
+        const int kd = comps.kind[j][c];
+        const double th = comps.thr[j][c], vm = comps.vmax[j][c];
+        const double omega = fmin(fmax(dq, -vm), vm);
+        if (kd == GXK_OMEGA) val = omega;
+        else if (kd == GXK_Q) val = q;
+        else if (kd == GXK_ONE) val = 1.0;
+        else
+        {
+          const double r = omega * comps.ithr[j][c];
+          if (kd == GXK_SAT) val = fmin(fmax(r, -1.0), 1.0);
+          else
+          {
+            const double sg = omega == 0.0 ? 0.0 : (omega > th ? 1.0 : (omega < -th ? -1.0 : r));
+            val = kd == GXK_SGN ? sg : omega * omega * sg;
+          }
+        }
+      }
+      o[c * 32] = val;
+    }
+  }
+}
+// component fragment of one k-step: lane (g, t) holds column g of joint J for sample 4 kk + t (zero behind the XC stored columns)
+template <int J, int XC>
+__device__ __forceinline__ double gram_load_xside(const double* __restrict__ side, int kk, int lane)
+{
+  const int g = lane >> 2, t = lane & 3;
+  return g < XC ? side[(J * XC + g) * 32 + 4 * kk + t] : 0.0;
+}
+template <int NJ, int PAR, int STEP, int Z, int XC>
+__device__ __forceinline__ void gram_ext_steps(const double* __restrict__ slot, const double* __restrict__ side, int ks, int lane,
+                                               const double (&bcur)[GramGeom<NJ, 0, Z>::T], double bxcur,
+                                               double (&acc)[GramGeom<NJ, 0, Z>::ntiles(GF_TS, PAR)][2],
+                                               double (&xacc)[GramGeom<NJ, 1, Z>::nxtiles(GF_TS, PAR)][2])
+{
+  using G = GramGeom<NJ, 0, Z>;
   constexpr int J = STEP / G::KPW;
   if constexpr (STEP + 1 < G::NSTEPS)
   {
     double bnext[G::T];
     constexpr int JN = (STEP + 1) / G::KPW;
     const int kn = ks * G::KPW + (STEP + 1) % G::KPW;
-    gram_load_frags<NJ, JN, 1>(slot, kn, lane, bnext);
-    const double bxn = gram_load_xfrag<NJ, JN>(slot, kn, lane);
-    gram_mma_step<NJ, PAR, J, 0>(bcur, acc);
-    gram_cross_step<NJ, PAR, J>(bcur, bxcur, xacc);
-    gram_ext_steps<NJ, PAR, STEP + 1>(slot, ks, lane, bnext, bxn, acc, xacc);
+    gram_load_frags<NJ, JN, 0, Z>(slot, kn, lane, bnext);
+    const double bxn = gram_load_xside<JN, XC>(side, kn, lane);
+    gram_mma_step<NJ, PAR, J, Z>(bcur, acc);
+    gram_cross_step<NJ, PAR, J, Z>(bcur, bxcur, xacc);
+    gram_ext_steps<NJ, PAR, STEP + 1, Z, XC>(slot, side, ks, lane, bnext, bxn, acc, xacc);
   }
   else
   {
-    gram_mma_step<NJ, PAR, J, 0>(bcur, acc);
-    gram_cross_step<NJ, PAR, J>(bcur, bxcur, xacc);
+    gram_mma_step<NJ, PAR, J, Z>(bcur, acc);
+    gram_cross_step<NJ, PAR, J, Z>(bcur, bxcur, xacc);
   }
 }
 
-template <int NJ, int SLOTS, int PAR>
-__device__ __forceinline__ void gram_ext_mma_role(const SamplesDev& in, double* smem, GramBars* bars, int ks, int lane)
+template <int NJ, int SLOTS, int PAR, int Z, int XC>
+__device__ __forceinline__ void gram_ext_mma_role(const SamplesDev& in, double* smem, const double* side0, GramBars* bars, int ks, int lane)
 {
-  using G = GramGeom<NJ, 1>;
-  using G0 = GramGeom<NJ>;
-  double acc[G0::ntiles(GF_TS, PAR)][2], xacc[G::nxtiles(GF_TS, PAR)][2];
+  using G0 = GramGeom<NJ, 0, Z>;
+  using GX = GramGeom<NJ, 1, Z>;
+  double acc[G0::ntiles(GF_TS, PAR)][2], xacc[GX::nxtiles(GF_TS, PAR)][2];
 #pragma unroll
   for (int k = 0; k < G0::ntiles(GF_TS, PAR); k++) acc[k][0] = acc[k][1] = 0.0;
 #pragma unroll
-  for (int k = 0; k < G::nxtiles(GF_TS, PAR); k++) xacc[k][0] = xacc[k][1] = 0.0;
+  for (int k = 0; k < GX::nxtiles(GF_TS, PAR); k++) xacc[k][0] = xacc[k][1] = 0.0;
   const int64_t ngroups = (in.n + 31) / 32;
   const int64_t nk = ngroups > blockIdx.x ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 #pragma unroll 1
@@ -400,27 +465,34 @@ __device__ __forceinline__ void gram_ext_mma_role(const SamplesDev& in, double* 
   {
     const int s = (int)(k % SLOTS);
     const uint32_t u = (uint32_t)(k / SLOTS);
-    const double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
+    const double* slot = smem + (size_t)s * G0::SLOT_DOUBLES;
+    const double* side = side0 + (size_t)s * gram_ext_side_doubles<NJ, XC>();
     wait_counter_ge(&bars->filled[s], u + 1);
-    double b0[G::T];
-    gram_load_frags<NJ, 0, 1>(slot, ks * G::KPW, lane, b0);
-    const double bx0 = gram_load_xfrag<NJ, 0>(slot, ks * G::KPW, lane);
-    gram_ext_steps<NJ, PAR, 0>(slot, ks, lane, b0, bx0, acc, xacc);
+    double b0[G0::T];
+    gram_load_frags<NJ, 0, 0, Z>(slot, ks * G0::KPW, lane, b0);
+    const double bx0 = gram_load_xside<0, XC>(side, ks * G0::KPW, lane);
+    gram_ext_steps<NJ, PAR, 0, Z, XC>(slot, side, ks, lane, b0, bx0, acc, xacc);
     __syncwarp();
     if (lane == 0) red_release_inc(&bars->drained[s]);
   }
-  gram_mma_reduce<NJ, PAR, 0>(acc, smem, ks, lane);                        // rigid-body tiles: smem[0, NT * 64)
-  gram_cross_reduce_smem<NJ, PAR>(xacc, smem + G0::NT * 64, ks, lane);    // cross tiles behind them
+  gram_mma_reduce<NJ, PAR, Z>(acc, smem, ks, lane);                           // rigid-body tiles: smem[0, NT * 64)
+  gram_cross_reduce_smem<NJ, PAR, Z>(xacc, smem + G0::NT * 64, ks, lane);    // cross tiles behind them
 }
 
-template <int NJ, int SLOTS, int GENS, bool REV>
+template <int NJ, int SLOTS, int GENS, bool REV, int XC>
 __global__ void __launch_bounds__(GramGeom<NJ>::threads(GENS), 1)
     gram_ext_kernel(const __grid_constant__ ChainDev<NJ> C, const __grid_constant__ GramComps comps, const SamplesDev in,
                     const double* __restrict__ tau_meas, double* __restrict__ partial)
 {
-  using G = GramGeom<NJ, 1>;
+  constexpr int Z = GF_ZCOL && REV ? 1 : 0;
+  using G0 = GramGeom<NJ, 0, Z>;
+  using GX = GramGeom<NJ, 1, Z>;
+  constexpr int NOUT = (G0::NT + GX::NXT) * 64;
+  constexpr int SIDE = gram_ext_side_doubles<NJ, XC>();
   extern __shared__ __align__(16) double smem[];
   __shared__ GramBars bars;
+  // the component columns of the groups in the slots live behind max(slots, reduction area)
+  double* const side0 = smem + (G0::SLOT_DOUBLES * SLOTS > NOUT ? G0::SLOT_DOUBLES * SLOTS : NOUT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < SLOTS)
   {
@@ -442,18 +514,23 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(GENS), 1)
       gen_load<NJ>(C, in, min(i, in.n - 1), cur);
       trig_all<NJ>(cur.q, cur.sv, cur.cv);
       wait_counter_ge(&bars.drained[s], GF_MMA_WARPS * u);
-      double* slot = smem + (size_t)s * G::SLOT_DOUBLES;
-      gram_generate<NJ, REV, 1>(C, &comps, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
-      if (i >= in.n) gram_zero_lane<NJ, 1>(slot, lane);
+      double* slot = smem + (size_t)s * G0::SLOT_DOUBLES;
+      double* side = side0 + (size_t)s * SIDE;
+      gram_component_side<NJ, XC>(comps, cur, side, lane);
+      gram_generate<NJ, REV, 0, Z>(C, nullptr, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
+      if (i >= in.n)
+      {
+        gram_zero_lane<NJ, 0, Z>(slot, lane);
+        for (int c = 0; c < NJ * XC; c++) side[c * 32 + lane] = 0.0;
+      }
       __syncwarp();
       if (lane == 0) st_release_u32(&bars.filled[s], u + 1);
     }
     return;
   }
   const int mma_id = warp, ks = mma_id % GF_KSPLIT;
-  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_ext_mma_role<NJ, SLOTS, 0>(in, smem, &bars, ks, lane);
-  else gram_ext_mma_role<NJ, SLOTS, 1>(in, smem, &bars, ks, lane);
-  constexpr int NOUT = (GramGeom<NJ>::NT + G::NXT) * 64;
+  if (GF_TS == 1 || mma_id < GF_KSPLIT) gram_ext_mma_role<NJ, SLOTS, 0, Z, XC>(in, smem, side0, &bars, ks, lane);
+  else gram_ext_mma_role<NJ, SLOTS, 1, Z, XC>(in, smem, side0, &bars, ks, lane);
   double* out = partial + (size_t)blockIdx.x * NOUT;
   for (int k = mma_id * 32 + lane; k < NOUT; k += 32 * GF_MMA_WARPS) out[k] = smem[k];
 }
@@ -759,21 +836,22 @@ __global__ void gram_ext_scatter_kernel(const double* __restrict__ G, const doub
 // xj / xs: reduced joint and slot of every component column.  One thread per (a in 0 .. P + Pc, cc).
 __global__ void gram_cross_finish_kernel(const double* __restrict__ X, const double* __restrict__ Tm, const int32_t* __restrict__ kof,
                                          const int32_t* __restrict__ xj, const int32_t* __restrict__ xs, int nj, int njr, int Pc,
-                                         double* __restrict__ gram, double* __restrict__ rhs, int accumulate)
+                                         double* __restrict__ gram, double* __restrict__ rhs, int accumulate, int zcol)
 {
   const int P = 10 * nj, Pr = 10 * njr, Pt = P + Pc;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (P + 1 + Pc) * Pc) return;
   const int a = e / Pc, cc = e % Pc;
   const int j = xj[cc], g = xs[cc];
-  auto tjf = [&](int k) { return (1 + 10 * (njr - k) + 7) / 8; };  // GramGeom::tj
+  auto tjf = [&](int k) { return (1 + 10 * (njr - k) - zcol + 7) / 8; };  // GramGeom::tj
   int tb = 0;  // first cross tile of joint j
   for (int k = 0; k < j; k++) tb += tjf(k) + 1;
   const int tjj = tjf(j);
   auto xval = [&](int col) -> double {  // reduced regular column `col` (Pr = tau) against (j, g)
-    const int pos = col == Pr ? 0 : 1 + 10 * (njr - 1 - col / 10) + col % 10;  // GramGeom::pos
+    const int p = col % 10;
+    const int pos = col == Pr ? 0 : 1 + 10 * (njr - 1 - col / 10) + (zcol ? (p == 0 ? 9 : p - 1) : p);  // GramGeom::pos
     const int I = pos >> 3;
-    return (pos >= 1 + 10 * (njr - j)) ? 0.0 : X[(size_t)(tb + I) * 64 + (pos & 7) * 8 + g];
+    return (pos >= 1 + 10 * (njr - j) - zcol) ? 0.0 : X[(size_t)(tb + I) * 64 + (pos & 7) * 8 + g];  // behind rowlen(j): an exact zero of Phi
   };
   if (a < P)
   {
@@ -805,27 +883,35 @@ __global__ void gram_cross_finish_kernel(const double* __restrict__ X, const dou
   }
 }
 
+// slots of the extended-model kernel: rigid-body rows + XC component columns per joint
+template <int NJ, int Z, int XC>
+constexpr int gf_slots_ext()
+{
+  return std::min<int>(GF_MAX_SLOTS, (int)((227 * 1024 - 256) / (sizeof(double) * (GramGeom<NJ, 0, Z>::SLOT_DOUBLES + gram_ext_side_doubles<NJ, XC>()))));
+}
 // single pass (gram_ext_kernel): rigid-body tiles -> Gt | bt | tst (full parameter vector), cross tiles -> xsum
-template <int NJ, bool REV>
+template <int NJ, bool REV, int XC>
 static cudaError_t launch_ext_nj(ChainHost& ch, const GramComps& gc, const SamplesDev& in, const double* tau_meas, double* Gt, double* bt, double* tst,
                                  double* xpart, double* xsum, cudaStream_t st)
 {
-  using G = GramGeom<NJ, 1>;
-  using G0 = GramGeom<NJ>;
-  constexpr int SLOTS = gf_slots<NJ, 1>();
+  constexpr int Z = GF_ZCOL && REV ? 1 : 0;  // as in the kernel
+  using G0 = GramGeom<NJ, 0, Z>;
+  using GX = GramGeom<NJ, 1, Z>;
+  constexpr int SLOTS = gf_slots_ext<NJ, Z, XC>();
+  static_assert(SLOTS >= 2, "the extended-model kernel needs two slots");
   constexpr int GENS = GF_TS == 2 ? 4 : SLOTS;  // 8 MMA + 4 generator warps (one per SM sub-partition) whatever the number of slots
-  constexpr int PSTRIDE = (G0::NT + G::NXT) * 64;
-  const size_t smem = sizeof(double) * (size_t)std::max(G::SLOT_DOUBLES * SLOTS, PSTRIDE);
-  cudaError_t e = cudaFuncSetAttribute(gram_ext_kernel<NJ, SLOTS, GENS, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr int PSTRIDE = (G0::NT + GX::NXT) * 64;
+  const size_t smem = sizeof(double) * ((size_t)std::max(G0::SLOT_DOUBLES * SLOTS, PSTRIDE) + (size_t)SLOTS * gram_ext_side_doubles<NJ, XC>());
+  cudaError_t e = cudaFuncSetAttribute(gram_ext_kernel<NJ, SLOTS, GENS, REV, XC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t ngroups = (in.n + 31) / 32;
   const int grid = (int)std::min<int64_t>(ch.sm_count, ngroups);
-  gram_ext_kernel<NJ, SLOTS, GENS, REV><<<grid, G0::threads(GENS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), gc, in, tau_meas, xpart);
+  gram_ext_kernel<NJ, SLOTS, GENS, REV, XC><<<grid, G0::threads(GENS), smem, st>>>(narrow_g<NJ>(ch.gram.fold), gc, in, tau_meas, xpart);
   count_launch();
   const int nred = (G0::NT * 64 + 255) / 256;
   if (ch.gram.fold_identity)
   {
-    gram_fused_reduce_kernel<<<nred, 256, 0, st>>>(xpart, grid, G0::T, G0::P, Gt, bt, tst, 0, 0, PSTRIDE);
+    gram_fused_reduce_kernel<<<nred, 256, 0, st>>>(xpart, grid, G0::T, G0::P, Gt, bt, tst, 0, Z, PSTRIDE);
     count_launch();
   }
   else
@@ -833,12 +919,12 @@ static cudaError_t launch_ext_nj(ChainHost& ch, const GramComps& gc, const Sampl
     const int nj = ch.host.nj, Pr = G0::P;
     double* Gr = ch.gram.fold_dev + (size_t)nj * 100;
     double* br = Gr + (size_t)Pr * Pr;
-    gram_fused_reduce_kernel<<<nred, 256, 0, st>>>(xpart, grid, G0::T, G0::P, Gr, br, br + Pr, 0, 0, PSTRIDE);
+    gram_fused_reduce_kernel<<<nred, 256, 0, st>>>(xpart, grid, G0::T, G0::P, Gr, br, br + Pr, 0, Z, PSTRIDE);
     count_launch();
     e = launch_fold_expand(ch, Gt, bt, tst, 0, st);
     if (e != cudaSuccess) return e;
   }
-  gram_cross_reduce_kernel<<<(G::NXT * 64 + 255) / 256, 256, 0, st>>>(xpart + G0::NT * 64, grid, G::NXT * 64, PSTRIDE, xsum);
+  gram_cross_reduce_kernel<<<(GX::NXT * 64 + 255) / 256, 256, 0, st>>>(xpart + G0::NT * 64, grid, GX::NXT * 64, PSTRIDE, xsum);
   count_launch();
   return cudaGetLastError();
 }
@@ -878,9 +964,12 @@ cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const dou
   }
   bool rev = true;
   for (int j = 0; j < K; j++) rev = rev && F.joint[j].type == RDB_JOINT_REVOLUTE;
+  const int zc = GF_ZCOL && rev ? 1 : 0;  // GramGeom Z of the kernel that will run
+  int xcmax = 0;
+  for (int j = 0; j < K; j++) xcmax = std::max(xcmax, (int)gc.ncols[j]);
   int nxt = 0;
-  for (int j = 0; j < K; j++) nxt += (1 + 10 * (K - j) + 7) / 8 + 1;  // GramGeom::nxt
-  const int Tt = (10 * K + 8) / 8, ntt = Tt * (Tt + 1) / 2;            // GramGeom::T, NT
+  for (int j = 0; j < K; j++) nxt += (1 + 10 * (K - j) - zc + 7) / 8 + 1;  // GramGeom::nxt
+  const int Tt = (10 * K + 1 - zc + 7) / 8, ntt = Tt * (Tt + 1) / 2;      // GramGeom::T, NT
   // workspace: rigid block (P*P + P + 1) | cross sums (nxt*64) | per-CTA partials (sm_count*(ntt+nxt)*64) | component map (2 Pc ints)
   const size_t n_rigid = (size_t)P * P + P + 1, n_sum = (size_t)nxt * 64, n_part = (size_t)ch.sm_count * (ntt + nxt) * 64;
   cudaError_t e = grow(ch.gram.ext_dev, ch.gram.ext_bytes, sizeof(double) * (n_rigid + n_sum + n_part) + sizeof(int32_t) * 2 * (size_t)Pc);
@@ -895,13 +984,17 @@ cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const dou
   if (e != cudaSuccess) return e;
   switch (K)
   {
-#define X(N)                                                                                    \
-  case N:                                                                                       \
-  e = rev ? launch_ext_nj<N, true>(ch, gc, in, tau_meas, Gt, bt, tst, xpart, xsum, st)        \
-          : launch_ext_nj<N, false>(ch, gc, in, tau_meas, Gt, bt, tst, xpart, xsum, st);      \
+#define XL(N, R)                                                                                                  \
+  (xcmax <= 2 ? launch_ext_nj<N, R, 2>(ch, gc, in, tau_meas, Gt, bt, tst, xpart, xsum, st)                         \
+              : (xcmax <= 4 ? launch_ext_nj<N, R, 4>(ch, gc, in, tau_meas, Gt, bt, tst, xpart, xsum, st)           \
+                            : launch_ext_nj<N, R, 8>(ch, gc, in, tau_meas, Gt, bt, tst, xpart, xsum, st)))
+#define X(N)                                \
+  case N:                                   \
+  e = rev ? XL(N, true) : XL(N, false);     \
   break;
     X(1) X(2) X(3) X(4) X(5) X(6) X(7)
 #undef X
+#undef XL
   }
   if (e != cudaSuccess) return e;
   gram_ext_scatter_kernel<<<(P * (P + 1) + 255) / 256, 256, 0, st>>>(Gt, bt, tst, P, Pt, gram, rhs, tau_sq, accumulate);
@@ -910,7 +1003,7 @@ cudaError_t launch_gram_fused_ext(ChainHost& ch, const SamplesDev& in, const dou
   const int32_t* kof1 = ch.gram.fold_identity
                             ? nullptr
                             : reinterpret_cast<const int32_t*>(ch.gram.fold_dev + (size_t)nj * 100 + (size_t)(10 * K + 1) * (10 * K + 1));
-  gram_cross_finish_kernel<<<((P + 1 + Pc) * Pc + 127) / 128, 128, 0, st>>>(xsum, Tm1, kof1, dmap, dmap + Pc, nj, K, Pc, gram, rhs, accumulate);
+  gram_cross_finish_kernel<<<((P + 1 + Pc) * Pc + 127) / 128, 128, 0, st>>>(xsum, Tm1, kof1, dmap, dmap + Pc, nj, K, Pc, gram, rhs, accumulate, zc);
   count_launch();
   return cudaGetLastError();
 }
