@@ -368,12 +368,12 @@ __host__ __device__ constexpr int gram_ext_side_doubles()
 {
   return NJ * XC * 32;
 }
-// component columns of all joints for the lane's sample.  q_j, Dq_j are parked in the buffer itself (columns 1 and 0 of joint j; XC >= 2), then
-// ONE rolled loop over (joint, column) evaluates in place: ~100 instructions instead of 600 for six unrolled joints -- generator plus MMA
-// code of this kernel sit at the size where the instruction caches stop covering both (ncu: no_instruction 24 % of the generator's stalls
-// with the unrolled version)
+// component columns of all joints for the lane's sample.  q_j, Dq_j are parked in the buffer itself before the walk (columns 1 and 0 of joint
+// j; XC >= 2: nothing of them stays in registers through the walk); AFTER the walk ONE rolled loop over (joint, column) evaluates in place
+// (~100 instructions).  The order matters: with the loop between the wait for the slot and the walk the kernel ran at 1.02 G samples/s, with
+// the loop behind the walk at 1.21 (C6; ncu with the loop in front: no_instruction 23 % of the generator's stall samples).
 template <int NJ, int XC>
-__device__ __forceinline__ void gram_component_side(const GramComps& comps, const GenIn<NJ>& x, double* __restrict__ side, int lane)
+__device__ __forceinline__ void gram_component_park(const GenIn<NJ>& x, double* __restrict__ side, int lane)
 {
   static_assert(XC >= 2, "q and Dq of a joint are staged in its first two columns");
 #pragma unroll
@@ -382,6 +382,10 @@ __device__ __forceinline__ void gram_component_side(const GramComps& comps, cons
     side[(j * XC) * 32 + lane] = x.dq[j];
     side[(j * XC + 1) * 32 + lane] = x.q[j];
   }
+}
+template <int NJ, int XC>
+__device__ __forceinline__ void gram_component_side(const GramComps& comps, double* __restrict__ side, int lane)
+{
 #pragma unroll 1
   for (int j = 0; j < NJ; j++)
   {
@@ -516,8 +520,9 @@ __global__ void __launch_bounds__(GramGeom<NJ>::threads(GENS), 1)
       wait_counter_ge(&bars.drained[s], GF_MMA_WARPS * u);
       double* slot = smem + (size_t)s * G0::SLOT_DOUBLES;
       double* side = side0 + (size_t)s * SIDE;
-      gram_component_side<NJ, XC>(comps, cur, side, lane);
+      gram_component_park<NJ, XC>(cur, side, lane);
       gram_generate<NJ, REV, 0, Z>(C, nullptr, cur, in, tau_meas, slot, min(i, in.n - 1), lane);
+      gram_component_side<NJ, XC>(comps, side, lane);
       if (i >= in.n)
       {
         gram_zero_lane<NJ, 0, Z>(slot, lane);
