@@ -130,3 +130,36 @@ def test_extended_gram_on_folded_and_mixed_chains(name):
     assert_close(G.cpu().numpy() / np.max(np.abs(G_ref)), G_ref / np.max(np.abs(G_ref)), "extended gram", 1e-11)
     assert_close(b.cpu().numpy() / np.max(np.abs(b_ref)), b_ref / np.max(np.abs(b_ref)), "extended rhs", 1e-11)
     assert bool((G == G.T).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,ctype", [("c6", 1), ("c7", 1), ("c6", 3), ("random_b", 1)])
+def test_extended_gram_two_column_components(name, ctype):
+    """One two-column component (friction_polynomial1 or ideal spring) on every joint: the narrow side buffer of the one-pass kernel (4 slots
+    for 6 joints), ragged batch, against the oracle's regressor and component columns contracted in numpy."""
+    import torch
+    from oracle.oracle import OracleChain
+    from rosdyn_b200.chain import Chain
+    d = fixtures.by_name(name)
+    ch, oc = Chain(d), OracleChain(d)
+    n_in = d.n_inputs
+    comps = [(ctype, k, 0.05, 0.7) for k in range(n_in)]
+    tn = {1: "friction1", 3: "spring"}
+    pc = ch.setComponents([{"type": tn[t], "joint": j, "min_velocity": lo, "max_velocity": hi} for t, j, lo, hi in comps])
+    assert pc == 2 * n_in
+    n = 4099  # ends inside a group and inside a k-step
+    rng = np.random.RandomState(5)
+    q, dq, ddq = (rng.uniform(-1, 1, (n_in, n)) for _ in range(3))
+    dq[:, :3] = 0.0
+    phi, tau_r = oc.regressor_torque(q, dq, ddq)
+    ref_c = oracle.components_regressor(comps, n_in, q, dq)
+    P = 10 * d.n_joints
+    X = np.concatenate([phi.reshape(P, n_in, n), ref_c.reshape(pc, n_in, n)], axis=0)
+    G_ref = np.einsum("ari,bri->ab", X, X)
+    b_ref = np.einsum("ari,ri->a", X, tau_r)
+    G, b, tt = ch.regressorGramExt(*(torch.tensor(x, device="cuda") for x in (q, dq, ddq)))
+    assert_close(G.cpu().numpy() / np.max(np.abs(G_ref)), G_ref / np.max(np.abs(G_ref)), "extended gram", 1e-11)
+    assert_close(b.cpu().numpy() / np.max(np.abs(b_ref)), b_ref / np.max(np.abs(b_ref)), "extended rhs", 1e-11)
+    assert bool((G == G.T).all())
+    G2, b2, _ = ch.regressorGramExt(*(torch.tensor(x, device="cuda") for x in (q, dq, ddq)))
+    assert torch.equal(G, G2) and torch.equal(b, b2)
