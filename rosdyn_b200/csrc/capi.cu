@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -250,6 +251,8 @@ void rdb_chain_destroy(rdb_chain* chain)
   if (chain->gram.ext_dev) cudaFree(chain->gram.ext_dev);
   if (chain->host_arena.base) cudaFree(chain->host_arena.base);
   if (chain->host_arena.map_h) cudaFreeHost(chain->host_arena.map_h);
+  for (int k = 0; k < GramHostPipe::NSLOT; k++)
+    if (chain->gram_host.pin[k]) cudaFreeHost(chain->gram_host.pin[k]);
   for (int k = 0; k < 2; k++)
     if (chain->host_arena.st[k]) cudaStreamDestroy(chain->host_arena.st[k]);
   GramHostPipe& hp = chain->gram_host;
@@ -954,6 +957,40 @@ rdb_status rdb_regressor_gram_batch_host(rdb_chain* chain, const rdb_samples* in
   }
   else if (in->n == 0)
     RDB_CUDA(cudaMemsetAsync(dG, 0, sizeof(double) * n_out, hp.comp));
+  // Pageable inputs: gather each chunk into a pinned bounce buffer with a few host threads (one plane slice per task), then ONE contiguous
+  // asynchronous copy -- the driver would otherwise stage every cudaMemcpy2DAsync synchronously through its own buffer on one thread.
+  bool bounce = false;
+  if (in->n >= (1 << 14) && n_in > 0 && !hp.pin_failed)
+  {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, in->q) == cudaSuccess && at.type == cudaMemoryTypeUnregistered) bounce = true;
+    else cudaGetLastError();
+  }
+  const size_t slot_doubles = 4 * (size_t)std::max(n_in, 1) * chunk;
+  if (bounce && hp.pin_doubles < slot_doubles)
+  {
+    for (int s = 0; s < GramHostPipe::NSLOT; s++)
+    {
+      if (hp.pin[s]) cudaFreeHost(hp.pin[s]);
+      hp.pin[s] = nullptr;
+    }
+    hp.pin_doubles = 0;
+    bool ok = true;
+    for (int s = 0; s < GramHostPipe::NSLOT && ok; s++) ok = cudaHostAlloc(&hp.pin[s], sizeof(double) * slot_doubles, cudaHostAllocDefault) == cudaSuccess;
+    if (ok) hp.pin_doubles = slot_doubles;
+    else
+    {
+      cudaGetLastError();
+      for (int s = 0; s < GramHostPipe::NSLOT; s++)
+      {
+        if (hp.pin[s]) cudaFreeHost(hp.pin[s]);
+        hp.pin[s] = nullptr;
+      }
+      hp.pin_failed = true;  // no pinned memory to spare: the driver's staging serves
+      bounce = false;
+    }
+  }
+  const int n_workers = bounce ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 0;
   int64_t k = 0;
   for (int64_t off = 0; off < in->n; off += chunk, k++)
   {
@@ -962,10 +999,30 @@ rdb_status rdb_regressor_gram_batch_host(rdb_chain* chain, const rdb_samples* in
     if (k >= GramHostPipe::NSLOT) RDB_CUDA(cudaStreamWaitEvent(hp.copy, hp.freed[slot], 0));
     double* base = hp.stage[slot];
     const double* src[4] = {in->q, in->dq, in->ddq, tau_meas};
-    for (int a = 0; a < 4; a++)
-      if (src[a] && n_in > 0)
-        RDB_CUDA(cudaMemcpy2DAsync(base + (size_t)a * n_in * chunk, chunk * sizeof(double), src[a] + off, in->ld * sizeof(double),
-                                   len * sizeof(double), n_in, cudaMemcpyHostToDevice, hp.copy));
+    if (bounce)
+    {
+      if (k >= GramHostPipe::NSLOT) RDB_CUDA(cudaEventSynchronize(hp.copied[slot]));  // the previous copy out of this bounce buffer is done
+      double* pb = hp.pin[slot];
+      const int n_arr = tau_meas ? 4 : 3, n_tasks = n_arr * n_in;
+      std::atomic<int> next{0};
+      auto work = [&] {
+        for (int t = next.fetch_add(1); t < n_tasks; t = next.fetch_add(1))
+        {
+          const int a = t / n_in, r = t % n_in;
+          memcpy(pb + ((size_t)a * n_in + r) * chunk, src[a] + (size_t)r * in->ld + off, sizeof(double) * (size_t)len);
+        }
+      };
+      std::vector<std::thread> pool;
+      for (int w = 1; w < n_workers; w++) pool.emplace_back(work);
+      work();
+      for (std::thread& th : pool) th.join();
+      RDB_CUDA(cudaMemcpyAsync(base, pb, sizeof(double) * (size_t)n_arr * n_in * chunk, cudaMemcpyHostToDevice, hp.copy));
+    }
+    else
+      for (int a = 0; a < 4; a++)
+        if (src[a] && n_in > 0)
+          RDB_CUDA(cudaMemcpy2DAsync(base + (size_t)a * n_in * chunk, chunk * sizeof(double), src[a] + off, in->ld * sizeof(double),
+                                     len * sizeof(double), n_in, cudaMemcpyHostToDevice, hp.copy));
     RDB_CUDA(cudaEventRecord(hp.copied[slot], hp.copy));
     RDB_CUDA(cudaStreamWaitEvent(hp.comp, hp.copied[slot], 0));
     rdb_samples v{len, chunk, base, base + (size_t)n_in * chunk, base + (size_t)2 * n_in * chunk, nullptr};
