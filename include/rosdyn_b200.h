@@ -349,8 +349,8 @@ rdb_status rdb_group_synchronize(rdb_group* group);
  * The handle is NOT const here: the staging buffers, streams and events of these pipelines live in the handle (grown on demand, freed with
  * it).  Calls on one handle from several host threads are serialised by a per-handle lock (they do not race, they do not overlap either);
  * for concurrency use one handle per thread, as the reference does with Chain::clone() (P.h:554).  Pinned (cudaHostAlloc /
- * cudaHostRegister) buffers overlap the copies with the kernels; pageable buffers work: rdb_regressor_gram_batch_host gathers them into pinned
- * bounce buffers of the handle with a few host threads (0.62 of the link's rate), the other entries leave the staging to the driver (slower).
+ * cudaHostRegister) buffers overlap the copies with the kernels at the link's rate; pageable buffers work: the entries gather / scatter them
+ * through pinned bounce buffers of the handle with a few host threads (0.5 - 0.6 of the link's rate; the driver's own staging reaches 0.2 - 0.3).
  * Calls whose arrays fit 256 KB in all (a handful of samples) skip the copies: the handle packs them into a mapped pinned buffer of its own
  * and the kernels work on it in place -- one launch and one synchronisation, 16-28 us per call on a B200 host (profiles/r02_latency.txt). */
 rdb_status rdb_kinematics_batch_host(rdb_chain* chain, const rdb_samples* in, const rdb_kinematics_out* out);

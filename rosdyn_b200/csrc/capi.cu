@@ -251,6 +251,7 @@ void rdb_chain_destroy(rdb_chain* chain)
   if (chain->gram.ext_dev) cudaFree(chain->gram.ext_dev);
   if (chain->host_arena.base) cudaFree(chain->host_arena.base);
   if (chain->host_arena.map_h) cudaFreeHost(chain->host_arena.map_h);
+  if (chain->host_arena.pin) cudaFreeHost(chain->host_arena.pin);
   for (int k = 0; k < GramHostPipe::NSLOT; k++)
     if (chain->gram_host.pin[k]) cudaFreeHost(chain->gram_host.pin[k]);
   for (int k = 0; k < 2; k++)
@@ -634,7 +635,34 @@ struct Plane
   bool records = false;  // RDB_LAYOUT_EIGEN output: [sample][planes] dense records on both sides (one contiguous copy per chunk)
   double* d[2] = {nullptr, nullptr};
   double* hm = nullptr;  // mapped mode: host alias of d[0]
+  double* hp[2] = {nullptr, nullptr};  // bounce mode: pinned mirror of d[slot]
 };
+
+// n_tasks independent pieces of host work on a few threads (gather / scatter of plane slices between caller memory and pinned buffers)
+template <class F>
+static void host_parallel(int64_t n_tasks, F&& task)
+{
+  const int n_workers = (int)std::min<int64_t>(n_tasks, std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2)));
+  std::atomic<int64_t> next{0};
+  auto work = [&] {
+    for (int64_t t = next.fetch_add(1); t < n_tasks; t = next.fetch_add(1)) task(t);
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < n_workers; w++) pool.emplace_back(work);
+  work();
+  for (std::thread& th : pool) th.join();
+}
+static bool is_pageable(const void* p)
+{
+  if (!p) return false;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
+}
 
 struct HostPipe
 {
@@ -648,11 +676,29 @@ struct HostPipe
     int64_t off, len;
   };
   std::vector<Pending> pending;  // mapped mode: outputs to hand to the caller after the synchronisation
+  bool bounce = false;           // pageable caller memory: every transfer goes through the pinned mirror of the arena
+  std::vector<Pending> waiting[2];  // bounce mode: outputs of the last chunk of a slot, still to be scattered to the caller
   // device buffers and streams come from the handle's arena (grown on demand, freed with the handle); one host call at a time per handle
   rdb_status init(HostArena& ar, int64_t n, int64_t chunk_max, std::vector<Plane*> planes)
   {
     all = planes;
     chunk = std::min<int64_t>(std::max<int64_t>(n, 1), chunk_max);
+    if (!ar.pin_failed && n >= (1 << 12))
+      for (Plane* p : all)
+        if (p->planes > 0 && (is_pageable(p->h_in) || is_pageable(p->h_out)))
+        {
+          bounce = true;
+          break;
+        }
+    if (bounce)
+    {
+      // at most 64 MB of pinned memory per slot
+      int64_t total = 0;
+      for (Plane* p : all)
+        if ((p->h_in || p->h_out) && p->planes > 0) total += p->planes;
+      const int64_t cap = std::max<int64_t>(1024, ((int64_t)(64 << 20) / (8 * std::max<int64_t>(total, 1))) & ~(int64_t)1023);
+      chunk = std::min(chunk, cap);
+    }
     const int slots = n > chunk ? 2 : 1;
     for (int k = 0; k < 2; k++)
     {
@@ -698,15 +744,63 @@ struct HostPipe
       RDB_CUDA(cudaMalloc(&ar.base, need));
       ar.bytes = need;
     }
+    if (bounce && ar.pin_bytes < need)
+    {
+      if (ar.pin) cudaFreeHost(ar.pin);
+      ar.pin = nullptr;
+      ar.pin_bytes = 0;
+      if (cudaHostAlloc(&ar.pin, need, cudaHostAllocDefault) == cudaSuccess) ar.pin_bytes = need;
+      else
+      {
+        cudaGetLastError();
+        ar.pin = nullptr;
+        ar.pin_failed = true;  // no pinned memory to spare: the driver's staging serves
+        bounce = false;
+      }
+    }
     double* cur = ar.base;
+    double* hcur = ar.pin;
     for (Plane* p : all)
       if ((p->h_in || p->h_out) && p->planes > 0)
         for (int k = 0; k < slots; k++)
         {
           p->d[k] = cur;
           cur += (size_t)p->planes * chunk;
+          if (bounce)
+          {
+            p->hp[k] = hcur;
+            hcur += (size_t)p->planes * chunk;
+          }
         }
     return RDB_OK;
+  }
+  // bounce mode: hand the outputs of the previous chunk of this slot to the caller (its copies into the pinned mirror are awaited here, while
+  // the other slot's chunk keeps the device busy)
+  rdb_status begin(int slot)
+  {
+    if (!bounce) return RDB_OK;
+    RDB_CUDA(cudaStreamSynchronize(st[slot]));  // also covers the previous copy OUT of this slot's pinned input regions
+    scatter(slot);
+    return RDB_OK;
+  }
+  void scatter(int slot)
+  {
+    for (const Pending& q : waiting[slot])
+    {
+      const Plane& p = *q.p;
+      const double* src = p.hp[slot];
+      if (p.records)
+      {
+        const int64_t total = q.len * p.planes, piece = (total + 15) / 16;
+        host_parallel(16, [&](int64_t t) {
+          const int64_t a = t * piece, b = std::min(total, a + piece);
+          if (a < b) memcpy(p.h_out + q.off * p.planes + a, src + a, sizeof(double) * (size_t)(b - a));
+        });
+      }
+      else
+        host_parallel(p.planes, [&](int64_t r) { memcpy(p.h_out + r * p.ld + q.off, src + r * chunk, sizeof(double) * (size_t)q.len); });
+    }
+    waiting[slot].clear();
   }
   rdb_status h2d(Plane& p, int slot, int64_t off, int64_t len)
   {
@@ -714,6 +808,15 @@ struct HostPipe
     if (mapped)
     {
       for (int64_t r = 0; r < p.planes; r++) memcpy(p.hm + r * chunk, p.h_in + r * p.ld + off, sizeof(double) * (size_t)len);
+      return RDB_OK;
+    }
+    if (bounce)
+    {
+      // the previous copy out of this pinned region belongs to the chunk begin(slot) has waited for, or to one that ran before its kernel
+      double* dst = p.hp[slot];
+      host_parallel(p.planes, [&](int64_t r) { memcpy(dst + r * chunk, p.h_in + r * p.ld + off, sizeof(double) * (size_t)len); });
+      RDB_CUDA(cudaMemcpy2DAsync(p.d[slot], chunk * sizeof(double), dst, chunk * sizeof(double), len * sizeof(double), p.planes,
+                                 cudaMemcpyHostToDevice, st[slot]));
       return RDB_OK;
     }
     RDB_CUDA(cudaMemcpy2DAsync(p.d[slot], chunk * sizeof(double), p.h_in + off, p.ld * sizeof(double), len * sizeof(double), p.planes,
@@ -728,6 +831,16 @@ struct HostPipe
       pending.push_back({&p, off, len});
       return RDB_OK;
     }
+    if (bounce)
+    {
+      if (p.records)
+        RDB_CUDA(cudaMemcpyAsync(p.hp[slot], p.d[slot], sizeof(double) * (size_t)len * p.planes, cudaMemcpyDeviceToHost, st[slot]));
+      else
+        RDB_CUDA(cudaMemcpy2DAsync(p.hp[slot], chunk * sizeof(double), p.d[slot], chunk * sizeof(double), len * sizeof(double), p.planes,
+                                   cudaMemcpyDeviceToHost, st[slot]));
+      waiting[slot].push_back({&p, off, len});
+      return RDB_OK;
+    }
     if (p.records)
       RDB_CUDA(cudaMemcpyAsync(p.h_out + off * p.planes, p.d[slot], sizeof(double) * (size_t)len * p.planes, cudaMemcpyDeviceToHost, st[slot]));
     else
@@ -739,6 +852,8 @@ struct HostPipe
   {
     for (int k = 0; k < 2; k++)
       if (st[k] && (k == 0 || !mapped)) RDB_CUDA(cudaStreamSynchronize(st[k]));
+    if (bounce)
+      for (int k = 0; k < 2; k++) scatter(k);
     for (const Pending& q : pending)
     {
       const Plane& p = *q.p;
@@ -812,6 +927,7 @@ rdb_status rdb_kinematics_batch_host(rdb_chain* chain, const rdb_samples* in, co
   for (int64_t off = 0; off < in->n; off += pipe.chunk, slot ^= 1)
   {
     const int64_t len = std::min<int64_t>(pipe.chunk, in->n - off);
+    RDB_TRY(pipe.begin(slot));
     RDB_TRY(pipe.h2d(hi.q, slot, off, len));
     RDB_TRY(pipe.h2d(hi.dq, slot, off, len));
     RDB_TRY(pipe.h2d(hi.ddq, slot, off, len));
@@ -848,6 +964,7 @@ static rdb_status dyn_host(rdb_chain* chain, const rdb_samples* in, double* phi,
   for (int64_t off = 0; off < in->n; off += pipe.chunk, slot ^= 1)
   {
     const int64_t len = std::min<int64_t>(pipe.chunk, in->n - off);
+    RDB_TRY(pipe.begin(slot));
     RDB_TRY(pipe.h2d(hi.q, slot, off, len));
     RDB_TRY(pipe.h2d(hi.dq, slot, off, len));
     RDB_TRY(pipe.h2d(hi.ddq, slot, off, len));

@@ -72,6 +72,11 @@ struct HostArena
   double* map_h = nullptr;
   double* map_d = nullptr;
   bool map_failed = false;
+  // pageable callers: pinned mirror of the device arena; host threads gather inputs into it / scatter outputs out of it, so that every copy
+  // to or from the device is asynchronous and contiguous (the driver stages copies on pageable memory synchronously on one thread)
+  double* pin = nullptr;
+  size_t pin_bytes = 0;
+  bool pin_failed = false;
 };
 constexpr size_t RDB_HOST_MAPPED_BYTES = 256 << 10;
 
