@@ -272,3 +272,49 @@ def test_gpu_ik_against_committed_reference_outputs(name):
     ok = (stat == 1) & same
     assert same.mean() > 0.97 and ok.mean() > 0.9           # knife-edge active-set decisions may differ by rounding on a sample or two
     assert np.max(np.abs(sol[:, ok] - g["sol"][:, ok])) <= 1e-8
+
+
+@pytest.mark.parametrize("name", GOLDEN_IK)
+def test_committed_reference_ik_against_an_independent_loop(name):
+    """The golden IK outputs were produced by the reference's loop around a stand-in QP (oracle/box_qp.h: the active-set method the oracle and the
+    CUDA kernel also use).  Here the loop is re-run in numpy around a DIFFERENT solver -- brute-force enumeration of the active sets, every
+    candidate from a dense linear solve -- with an independent rotation logarithm for the frame distance: same convergence flags, iteration
+    counts and solutions on the first targets of every golden file, so the goldens do not merely agree with themselves."""
+    from oracle.oracle import OracleChain
+    g = _golden_ik(name)
+    oc = OracleChain(fixtures.by_name(name))
+    n_in = g["seed"].shape[0]
+    toll, max_iter = float(g["toll"]), int(g["max_iter"])
+    checked = 0
+    for i in range(8):
+        Ta = g["target"][:, i].reshape(3, 4)
+        sol = g["seed"][:, i].copy()
+        done, it = 0, 0
+        while True:
+            K = oc.kinematics(sol[:, None], want=("T_tool", "jacobian"))
+            Tb = K["T_tool"][:, 0].reshape(3, 4)
+            J = K["jacobian"][:, 0].reshape(n_in, 6).T            # plane 6 a + k = row k of column a
+            e = np.concatenate([Ta[:, 3] - Tb[:, 3], -Ta[:, :3] @ _rot_log(Ta[:, :3].T @ Tb[:, :3])])
+            if np.linalg.norm(e) < toll:
+                done = 1
+                break
+            if it >= max_iter:
+                break
+            H, f = J.T @ J, -J.T @ e
+            if np.linalg.cond(H) > 1e10:
+                break                                              # singular J^T J: the minimiser is a face, solvers may differ
+            dq = _brute_box_qp(H, f, g["q_min"] - sol, g["q_max"] - sol)
+            sol = sol + dq
+            it += 1
+        else:
+            continue
+        if not done and it < max_iter:
+            continue                                               # left at a singular step: nothing to compare
+        assert done == g["status"][i], (name, i)
+        if done:
+            # independent rounding in the rotation logarithm can move a step across the tolerance: one iteration more or less, and two
+            # solutions that both meet |e| < toll differ by up to toll / sigma_min(J)
+            assert abs(it - int(g["iters"][i])) <= 1, (name, i, it, g["iters"][i])
+            assert np.max(np.abs(sol - g["sol"][:, i])) <= 1e-6, (name, i)
+        checked += 1
+    assert checked >= 4
