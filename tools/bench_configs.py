@@ -2,7 +2,7 @@
 """Every BASELINE.json config AT ITS STATED SIZE, one JSON line per config, each with a `clocks` record sampled during its timed region.
 bench.py stays the headline line; this is the table behind DESIGN.md section 5.
 
-  python tools/bench_configs.py [--configs 1,2,3,4,5,h] [--min-seconds 1.0]  > gpurun_out/configs.jsonl
+  python tools/bench_configs.py [--configs 1,2,3,4,5,h,g,x] [--min-seconds 1.0]  > gpurun_out/configs.jsonl
   torchrun --nproc-per-node 8 tools/bench_configs.py --configs 4,5            (configs 4 and 5 "on 8 B200": weak shards, config 4 + all-reduce)
 
   1  C6, N = 1e4, getJointTorque + getRegressor on the CPU: 1 thread and all cores, -O3 and -Ofast builds of the restatement and the
@@ -58,7 +58,7 @@ def cpu_config1(out):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,2,3,4,5,h,g")
+    ap.add_argument("--configs", default="1,2,3,4,5,h,g,x")
     ap.add_argument("--min-seconds", type=float, default=1.0)
     ap.add_argument("--scale", type=float, default=1.0, help="multiply every sample count (smoke runs)")
     args = ap.parse_args()
@@ -293,6 +293,25 @@ def main():
             sec, passes, clk = timed(pe, total)
             report("headline (materialised, RDB_LAYOUT_EIGEN records): C6, 1e8 samples, getRegressor + torque", total, sec, passes, clk,
                    bytes_per_sample=8 * (18 + 420 + 6), chunks=len(smps))
+    # ------------------------------------------------------------------ extended model [Phi | Phi_c] (N2): one friction component per joint
+    if "x" in want and world == 1:
+        for cname in ("c6", "c7"):
+            d = fixtures.by_name(cname)
+            ch = Chain(d)
+            ch.setComponents([{"type": "friction1", "joint": j, "min_velocity": 0.01, "max_velocity": 2.0} for j in ch.getActiveJointsName()])
+            n_in, total = d.n_inputs, N(1e8)
+            q, dq, ddq = inputs(n_in, total, 6)
+            Pt = 10 * d.n_joints + 2 * n_in
+
+            def px():
+                ch.regressorGramExt(q, dq, ddq)
+            sec, passes, clk = timed(px, total)
+            report(f"extended model: {cname.upper()}, 1e8 samples, fused [Phi | Phi_c] -> normal equations ({Pt} x {Pt}), friction_polynomial1 on every joint "
+                   f"[gram_ext_kernel<{n_in}>]", total, sec, passes, clk,
+                   flop_per_sample=n_in * Pt * (Pt + 1) + 2 * n_in * Pt,
+                   note="algorithmic flops of the dense n_act x (10 nJ + components) regressor (SYRK + GEMV convention)")
+            del q, dq, ddq, ch
+            torch.cuda.empty_cache()
     # ------------------------------------------------------------------ chains the unrolled kernels do not cover (> 8 moving joints): *_kernel_generic
     if "g" in want and world == 1:
         d = fixtures.random_chain(909, 12, p_prismatic=0.1, p_fixed=0.0)   # 12 moving joints: runtime loops, model in global memory
