@@ -394,7 +394,7 @@ __device__ __forceinline__ void gram_component_side(const GramComps& comps, doub
     double* o = side + (j * XC) * 32 + lane;
     const double dq = o[0], q = o[32];
     const int nc = comps.ncols[j];
-#pragma unroll 1
+#pragma unroll(XC <= 4 ? XC : 1)  // narrow sets: the columns of a joint evaluate side by side (their table reads and chains overlap)
     for (int c = 0; c < XC; c++)
     {
       double val = 0.0;
