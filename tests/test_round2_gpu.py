@@ -344,3 +344,32 @@ def test_small_host_calls_use_the_same_kernels(n, layout, torch):
     bq, bdq, bddq = (fill_uniform(d.n_inputs, big, 0x5EED0000 + 708, s) for s in range(3))
     tb = ch.getJointTorque(bq, bdq, bddq)
     assert np.array_equal(tb[:, :1000], _np(ch.getJointTorque(*(torch.tensor(x[:, :1000].copy(), device="cuda") for x in (bq, bdq, bddq)))))
+
+
+@pytest.mark.parametrize("layout", ["soa", "eigen"])
+def test_pageable_host_calls_through_the_pinned_bounce_buffers(layout, torch):
+    """numpy (pageable) arrays large enough for several chunks: the host entries gather / scatter them through the pinned mirror of the staging
+    arena with host threads (HostPipe::bounce); results bit-identical to the device entries, for plane and record layouts, ragged last chunk."""
+    from oracle.oracle import fill_uniform
+    from rosdyn_b200.chain import Chain
+    d = fixtures.by_name("c6")
+    ch = Chain(d)
+    n = 40_001
+    hq, hdq, hddq, hdddq = (fill_uniform(d.n_inputs, n, 0x5EED0000 + 808, s) for s in range(4))
+    dev = [torch.tensor(x, device="cuda") for x in (hq, hdq, hddq, hdddq)]
+    want = ("T_tool", "T_links", "jacobian", "twist", "dtwist", "ddtwist", "torque")
+    Kh = ch.kinematics(hq, hdq, hddq, hdddq, want=want, layout=layout)
+    Kd = ch.kinematics(*dev, want=want, layout=layout)
+    for k in want:
+        assert np.array_equal(Kh[k], _np(Kd[k])), k
+    Dh = ch.dynamics(hq, hdq, hddq, want=("regressor", "torque", "inertia"), layout=layout)
+    Dd = ch.dynamics(*dev[:3], want=("regressor", "torque", "inertia"), layout=layout)
+    for k in ("regressor", "torque", "inertia"):
+        assert np.array_equal(Dh[k], _np(Dd[k])), k
+    # a leading dimension larger than n on the host side (a view into a wider array)
+    wide = np.zeros((d.n_inputs, n + 77))
+    wide[:, :n] = hq
+    assert np.array_equal(ch.getJointTorque(wide[:, :n], hdq, hddq), _np(ch.getJointTorque(*dev[:3])))
+    Gh, bh, th = ch.regressorGram(hq, hdq, hddq)
+    Gd, bd, td = ch.regressorGram(*dev[:3])
+    assert np.max(np.abs(Gh - _np(Gd))) <= 1e-12 * np.max(np.abs(Gh)) and np.max(np.abs(bh - _np(bd))) <= 1e-12 * np.max(np.abs(bh))
